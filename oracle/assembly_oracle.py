@@ -1,0 +1,432 @@
+"""CPU ORACLE (test infrastructure, NOT product code) for the distributed assembly + mul! path.
+
+A numpy restatement of the reference algorithm, function by function (SURVEY.md section 8a rows
+A1-A14).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product path never does.
+
+PARITY STATUS -- "parity unpinned at entry level": the reference (GridapDistributed.jl 0.4.x) is
+Julia, cannot run in this image, and its own tests hold NO golden matrices, patterns or index maps
+(SURVEY.md section 8c).  The arithmetic of the path lives in un-vendored dependencies --
+Gridap.jl >=0.20.8,<0.21, PartitionedArrays.jl >=0.3.3,<0.4, SparseMatricesCSR.jl 0.6.6
+(reference Project.toml:19-31) -- whose published algorithms are restated here ("[ext]" below).
+The oracle is pinned by every known-answer test the reference's tests DO hold for this path
+(tests/test_oracle_kats.py): solution error < 1e-9 for u=(x+y)^2 Q2 on 4x4 (2,2)
+(test/PoissonTests.jl:45), |sum(b)-length(b)| < 1e-12 (test/FESpacesTests.jl:66), local matrix
+size == local lengths (test/FESpacesTests.jl:29-31), FullyAssembledRows == SubAssembledRows
+(test/FESpacesTests.jl:73-76), mul! alpha/beta semantics (test/BlockPartitionedArraysTests.jl:70-77),
+plus analytic element matrices and nnz closed forms.
+
+All ids are 1-based like the reference; arrays are numpy.  Every part lives in this process
+(the reference's ``with_debug`` mode): "exchanges" are list shuffles.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------------------
+# A1  cell integration  ([ext] Gridap.integrate; called from reference CellData.jl:234-239)
+# ------------------------------------------------------------------------------------------------
+
+
+def gauss_legendre_01(n):
+    """n-point Gauss-Legendre rule on [0,1] (Gridap ``Measure(Ω,deg)``: n = ceil((deg+1)/2), A.4)."""
+    x, w = np.polynomial.legendre.leggauss(n)
+    return (x + 1.0) / 2.0, w / 2.0
+
+
+def lagrange_1d(order, x):
+    """Values and derivatives of the equispaced Lagrange basis of ``order`` on [0,1] at points x.
+    Node j sits at j/order.  Returns (val[len(x), order+1], der[len(x), order+1])."""
+    nodes = np.arange(order + 1) / order
+    x = np.asarray(x, dtype=np.float64)
+    val = np.ones((len(x), order + 1))
+    der = np.zeros((len(x), order + 1))
+    for j in range(order + 1):
+        for m in range(order + 1):
+            if m != j:
+                val[:, j] *= (x - nodes[m]) / (nodes[j] - nodes[m])
+        for i in range(order + 1):
+            if i == j:
+                continue
+            t = np.full(len(x), 1.0 / (nodes[j] - nodes[i]))
+            for m in range(order + 1):
+                if m != j and m != i:
+                    t *= (x - nodes[m]) / (nodes[j] - nodes[m])
+            der[:, j] += t
+    return val, der
+
+
+def reference_tables(D, order, ref_nodes, quad_degree):
+    """phi[q,i], dphi[q,i,a], w[q], xi[q,a] for the scalar tensor Lagrange basis whose local dof
+    order is given by ``ref_nodes`` (nd x D reference coordinates: SURVEY A.5, never hard-coded).
+    Quadrature points are x fastest (A.4)."""
+    n = (quad_degree + 2) // 2  # ceil((deg+1)/2)
+    x1, w1 = gauss_legendre_01(n)
+    val, der = lagrange_1d(order, x1)
+    tix = np.rint(np.asarray(ref_nodes) * order).astype(int)  # tensor index of every local dof
+    nd = len(tix)
+    nq = n**D
+    qidx = np.stack([(np.arange(nq) // n**d) % n for d in range(D)], axis=1)
+    xi = x1[qidx]
+    w = np.prod(w1[qidx], axis=1)
+    phi = np.ones((nq, nd))
+    dphi = np.ones((nq, nd, D))
+    for d in range(D):
+        phi *= val[qidx[:, d]][:, tix[:, d]]
+        for a in range(D):
+            src = der if a == d else val
+            dphi[:, :, a] *= src[qidx[:, d]][:, tix[:, d]]
+    return phi, dphi, w, xi
+
+
+def geometry_tables(D, xi):
+    """Q1 geometry map shape functions N[q,v] and gradients dN[q,v,a], vertices x fastest."""
+    nv = 2**D
+    vc = np.array([[(v >> d) & 1 for d in range(D)] for v in range(nv)], dtype=np.float64)
+    N = np.ones((len(xi), nv))
+    dN = np.ones((len(xi), nv, D))
+    for d in range(D):
+        f = np.where(vc[None, :, d] == 1, xi[:, None, d], 1.0 - xi[:, None, d])
+        g = np.where(vc[None, :, d] == 1, 1.0, -1.0) * np.ones_like(f)
+        N *= f
+        for a in range(D):
+            dN[:, :, a] *= g if a == d else f
+    return N, dN
+
+
+def integrate_cells(form, cell_coords, ref_nodes, order, ncomp, quad_degree, source=None, chunk=4096):
+    """Cell matrices K[c,i,j] (test i = row, trial j = col) and vectors f[c,i] by quadrature (A.4).
+
+    form: ("poisson",) | ("mass",) | ("elasticity", lam, mu).  cell_coords: (ncells, 2^D, D).
+    source: None | float | callable f(x[D,npts]) -> [npts] (scalar) or [ncomp,npts].
+    """
+    ncells, nv, D = cell_coords.shape
+    phi, dphi, w, xi = reference_tables(D, order, ref_nodes, quad_degree)
+    N, dN = geometry_tables(D, xi)
+    nds = phi.shape[1]
+    nd = nds * ncomp
+    K = np.zeros((ncells, nd, nd))
+    F = np.zeros((ncells, nd))
+    for s in range(0, ncells, chunk):
+        X = cell_coords[s : s + chunk]
+        J = np.einsum("cvd,qva->cqda", X, dN)  # J[d,a] = dx_d/dxi_a
+        detJ = np.linalg.det(J)
+        Jinv = np.linalg.inv(J)  # [a,d]
+        g = np.einsum("qia,cqad->cqid", dphi, Jinv)  # physical gradients
+        wd = w[None, :] * np.abs(detJ)
+        if form[0] == "poisson":
+            Ks = np.einsum("cq,cqid,cqjd->cij", wd, g, g)
+        elif form[0] == "mass":
+            Ks = np.einsum("cq,qi,qj->cij", wd, phi, phi)
+        elif form[0] == "elasticity":
+            lam, mu = form[1], form[2]
+            Kab = np.einsum("cq,cqia,cqjb->ciajb", wd, g, g)  # int d_a phi_i d_b phi_j
+            Ks = None
+            Kv = np.zeros((len(X), ncomp, nds, ncomp, nds))
+            lap = np.einsum("ciaja->cij", Kab)
+            for al in range(ncomp):
+                for be in range(ncomp):
+                    blk = lam * Kab[:, :, al, :, be] + mu * Kab[:, :, be, :, al]
+                    if al == be:
+                        blk = blk + mu * lap
+                    Kv[:, al, :, be, :] = blk
+            K[s : s + chunk] = Kv.reshape(len(X), nd, nd)
+        else:
+            raise ValueError(form)
+        if form[0] != "elasticity":
+            for c in range(ncomp):  # componentwise scalar forms
+                K[s : s + chunk, c * nds : (c + 1) * nds, c * nds : (c + 1) * nds] = Ks
+        if source is not None:
+            if callable(source):
+                xq = np.einsum("qv,cvd->dcq", N, X).reshape(D, -1)
+                fq = np.asarray(source(xq), dtype=np.float64)
+                fq = fq.reshape(ncomp, len(X), -1) if fq.ndim == 2 else np.broadcast_to(fq.reshape(1, len(X), -1), (ncomp, len(X), len(w)))
+            else:
+                fq = np.full((ncomp, len(X), len(w)), float(source))
+            for c in range(ncomp):
+                F[s : s + chunk, c * nds : (c + 1) * nds] = np.einsum("cq,qi,cq->ci", wd, phi, fq[c])
+    return K, F
+
+
+# ------------------------------------------------------------------------------------------------
+# A2  Dirichlet lifting  ([ext] collect_cell_matrix_and_vector(U,V,a,l,uhd); reference FESpaces.jl:703-715)
+# ------------------------------------------------------------------------------------------------
+
+
+def lift_dirichlet(K, F, cell_dof_ids, dirichlet_values):
+    """f_c <- f_c - K_c u_c with u_c = Dirichlet values on Dirichlet dofs, 0 on free dofs (A.7)."""
+    ids = cell_dof_ids
+    dv = np.asarray(dirichlet_values, dtype=np.float64)
+    u = np.where(ids < 0, dv[np.clip(-ids, 1, max(len(dv), 1)) - 1], 0.0) if len(dv) else np.zeros(ids.shape)
+    return F - np.einsum("cij,cj->ci", K, u)
+
+
+# ------------------------------------------------------------------------------------------------
+# A3  numeric loop  ([ext] add_entries!; reference FESpaces.jl:794-798, strategies :802-816,
+#      vector allocation Algebra.jl:808-821)
+# ------------------------------------------------------------------------------------------------
+
+
+def numeric_loop(cell_dof_ids_rows, cell_dof_ids_cols, K, F, nrows_local, row_is_ghost=None):
+    """Triplets in the reference's order: per cell, lj outer, li inner, ids<=0 skipped (A.3).
+    ``row_is_ghost`` (bool per FE-space local row) is the FullyAssembledRows mask
+    (``rows_local_to_ghost[row]==0``, FESpaces.jl:808-816); it masks vector rows too."""
+    rid, cid = cell_dof_ids_rows, cell_dof_ids_cols
+    rvalid = rid > 0
+    if row_is_ghost is not None:
+        rvalid &= ~row_is_ghost[np.maximum(rid, 1) - 1]
+    cvalid = cid > 0
+    ncells, ndr = rid.shape
+    ndc = cid.shape[1]
+    # order (cell, lj, li): build [c, lj, li] arrays
+    m = cvalid[:, :, None] & rvalid[:, None, :]
+    I = np.broadcast_to(rid[:, None, :], m.shape)[m].astype(np.int64)
+    J = np.broadcast_to(cid[:, :, None], m.shape)[m].astype(np.int64)
+    V = np.transpose(K, (0, 2, 1))[m]  # K[c, li, lj] viewed as [c, lj, li]
+    b = np.zeros(nrows_local)
+    touched = np.zeros(nrows_local, dtype=bool)
+    if F is not None:
+        # b[i] = b[i] + f[li] sequentially over cells (Algebra.jl:811-821): np.add.at is sequential
+        np.add.at(b, rid[rvalid] - 1, F[rvalid])
+        touched[rid[rvalid] - 1] = True
+    return I, J, V, b, touched
+
+
+# ------------------------------------------------------------------------------------------------
+# index-set helpers (reference Algebra.jl:919-1009, 1174-1257); an index set is a dict
+# ------------------------------------------------------------------------------------------------
+
+
+def local_indices(n_global, part, l2g, l2o):
+    l2g = np.asarray(l2g, dtype=np.int64)
+    l2o = np.asarray(l2o, dtype=np.int32)
+    own = l2o == part
+    o2l = np.flatnonzero(own) + 1
+    g2l_ = np.flatnonzero(~own) + 1
+    l2gh = np.zeros(len(l2g), dtype=np.int64)
+    l2gh[g2l_ - 1] = np.arange(1, len(g2l_) + 1)
+    return dict(n=int(n_global), part=int(part), l2g=l2g, l2o=l2o, own_to_local=o2l, ghost_to_local=g2l_,
+                local_to_ghost=l2gh, lookup=dict(zip(l2g.tolist(), range(1, len(l2g) + 1))))
+
+
+def own_and_ghost(n_global, part, own_to_global, ghost_to_global, ghost_to_owner):
+    l2g = np.concatenate([np.asarray(own_to_global, np.int64), np.asarray(ghost_to_global, np.int64)])
+    l2o = np.concatenate([np.full(len(own_to_global), part, np.int32), np.asarray(ghost_to_owner, np.int32)])
+    d = local_indices(n_global, part, l2g, l2o)
+    d.update(own_to_global=np.asarray(own_to_global, np.int64), ghost_to_global=np.asarray(ghost_to_global, np.int64),
+             ghost_to_owner=np.asarray(ghost_to_owner, np.int32))
+    return d
+
+
+def g2l(ids, gids):
+    lk = ids["lookup"]
+    return np.fromiter((lk.get(int(g), 0) for g in gids), dtype=np.int64, count=len(gids))
+
+
+def first_appearance_unique(a):
+    u, first = np.unique(a, return_index=True)
+    return u[np.argsort(first, kind="stable")]
+
+
+def ghost_lids_touched(ids, gids):  # Algebra.jl:931-962
+    lid = g2l(ids, gids)
+    gh = ids["local_to_ghost"][lid - 1]
+    return first_appearance_unique(gh[gh > 0])
+
+
+def find_gid_and_owner(ighost_to_jghost, jids):  # Algebra.jl:919-928 (note the sort at :923)
+    jl = np.sort(jids["ghost_to_local"][np.asarray(ighost_to_jghost, dtype=np.int64) - 1])
+    return jids["l2g"][jl - 1], jids["l2o"][jl - 1]
+
+
+def setup_prange_without_ghosts(dofs):  # Algebra.jl:1174-1183
+    return own_and_ghost(dofs["n"], dofs["part"], dofs["l2g"][dofs["own_to_local"] - 1], [], [])
+
+
+def setup_prange_with_ghosts(dofs, gids, owners=None):
+    own = dofs["l2g"][dofs["own_to_local"] - 1]
+    if owners is None:  # Algebra.jl:1191-1203
+        g, o = find_gid_and_owner(ghost_lids_touched(dofs, gids), dofs)
+    else:  # Algebra.jl:1210-1238: first appearance among entries whose column owner is not me
+        sel = owners != dofs["part"]
+        gs, os_ = gids[sel], owners[sel]
+        u, first = np.unique(gs, return_index=True)
+        order = np.argsort(first, kind="stable")
+        g, o = u[order], os_[first[order]]
+    return own_and_ghost(dofs["n"], dofs["part"], own, g, o)
+
+
+def assembly_neighbors(rows_all):
+    """[ext] parts_snd = sorted owners of my ghosts; parts_rcv = ascending parts that send to me."""
+    snd = [sorted(set(r["ghost_to_owner"].tolist())) for r in rows_all]
+    rcv = [[q + 1 for q, s in enumerate(snd) if (p + 1) in s] for p in range(len(rows_all))]
+    return snd, rcv
+
+
+# ------------------------------------------------------------------------------------------------
+# A6  ghost-row triplet migration (reference Algebra.jl:1048-1131)
+# ------------------------------------------------------------------------------------------------
+
+
+def assemble_coo_with_column_owner(I, J, V, rows_all, Jo):
+    P = len(I)
+    parts_snd, parts_rcv = assembly_neighbors(rows_all)
+    outbox = [dict() for _ in range(P)]
+    for p in range(P):
+        rows = rows_all[p]
+        li = g2l(rows, I[p])
+        owner = rows["l2o"][li - 1]
+        for q in parts_snd[p]:
+            k = np.flatnonzero(owner == q)  # in triplet order (:1072-1087)
+            outbox[p][q] = (I[p][k].copy(), J[p][k].copy(), Jo[p][k].copy(), V[p][k].copy())
+            V[p][k] = 0.0  # :1084 -- I,J stay, values zeroed
+    for p in range(P):
+        for q in parts_rcv[p]:  # appended in neighbour order (:1099-1112)
+            gi, gj, jo, v = outbox[q - 1][p + 1]
+            I[p] = np.concatenate([I[p], gi])
+            J[p] = np.concatenate([J[p], gj])
+            Jo[p] = np.concatenate([Jo[p], jo])
+            V[p] = np.concatenate([V[p], v])
+    return I, J, Jo, V
+
+
+# ------------------------------------------------------------------------------------------------
+# A9  COO -> CSR  ([ext] sparsecsr / sparse: stable sort, duplicates summed in sorted order)
+# ------------------------------------------------------------------------------------------------
+
+
+def coo_to_csr(I, J, V, m, n):
+    """Returns (rowptr[m+1], colind[nnz], nzval[nnz]) 0-based; explicit zeros are kept."""
+    I = np.asarray(I, np.int64) - 1
+    J = np.asarray(J, np.int64) - 1
+    order = np.lexsort((J, I))  # stable: equal (i,j) keep triplet order
+    Is, Js, Vs = I[order], J[order], np.asarray(V)[order]
+    if len(Is) == 0:
+        return np.zeros(m + 1, np.int64), np.zeros(0, np.int64), np.zeros(0)
+    new = np.ones(len(Is), dtype=bool)
+    new[1:] = (Is[1:] != Is[:-1]) | (Js[1:] != Js[:-1])
+    seg = np.cumsum(new) - 1
+    start = np.flatnonzero(new)
+    rank = np.arange(len(Is)) - start[seg]
+    vals = np.zeros(len(start))
+    for r in range(int(rank.max()) + 1):  # sequential left-to-right sum per duplicate group
+        s = rank == r
+        vals[seg[s]] += Vs[s]
+    rows = Is[start]
+    rowptr = np.zeros(m + 1, dtype=np.int64)
+    np.add.at(rowptr, rows + 1, 1)
+    return np.cumsum(rowptr), Js[start], vals
+
+
+# ------------------------------------------------------------------------------------------------
+# A11  right-hand side (reference Algebra.jl:720-753, 870-907) and PVector assemble! ([ext] A.9)
+# ------------------------------------------------------------------------------------------------
+
+
+def prange_from_touched(dofs, touched):  # Algebra.jl:870-896
+    lids = np.flatnonzero(touched) + 1
+    gh = dofs["local_to_ghost"][lids - 1]
+    g, o = find_gid_and_owner(gh[gh > 0], dofs)
+    return own_and_ghost(dofs["n"], dofs["part"], dofs["l2g"][dofs["own_to_local"] - 1], g, o)
+
+
+def rhs_callback(b_fespace, dofs, rows):  # Algebra.jl:720-753
+    b = np.zeros(len(rows["l2g"]))
+    nown = len(rows["own_to_local"])
+    b[:nown] = b_fespace[dofs["own_to_local"] - 1]  # :730 own values (same own order)
+    gl = g2l(dofs, rows["l2g"][nown:])  # :733-750
+    b[nown:] = b_fespace[gl - 1]
+    return b
+
+
+def assemble_pvector(b_all, rows_all):
+    """``assemble!(b)``: ghost -> owner with +, in neighbour order, then ghosts are zeroed (A.9)."""
+    P = len(b_all)
+    parts_snd, parts_rcv = assembly_neighbors(rows_all)
+    box = [dict() for _ in range(P)]
+    for p in range(P):
+        r = rows_all[p]
+        nown = len(r["own_to_local"])
+        for q in parts_snd[p]:
+            k = np.flatnonzero(r["ghost_to_owner"] == q)
+            box[p][q] = (r["ghost_to_global"][k], b_all[p][nown + k].copy())
+        b_all[p][nown:] = 0.0
+    for p in range(P):
+        for q in parts_rcv[p]:
+            g, v = box[q - 1][p + 1]
+            np.add.at(b_all[p], g2l(rows_all[p], g) - 1, v)
+    return b_all
+
+
+# ------------------------------------------------------------------------------------------------
+# A12  orchestration (reference Algebra.jl:593-646 SubAssembledRows, :549-579 FullyAssembledRows)
+# ------------------------------------------------------------------------------------------------
+
+
+def create_from_nz(strategy, I, J, V, b_fe, touched, test_dofs, trial_dofs):
+    """Per-part lists in, per-part (rows, cols, (rowptr,colind,nzval), b) out."""
+    P = len(I)
+    I = [np.array(x, np.int64) for x in I]
+    J = [np.array(x, np.int64) for x in J]
+    V = [np.array(x, np.float64) for x in V]
+    if strategy == "fully":
+        rows = [setup_prange_without_ghosts(d) for d in test_dofs]  # :556
+        b = [rhs_callback(b_fe[p], test_dofs[p], rows[p]) for p in range(P)] if b_fe is not None else None
+        I = [test_dofs[p]["l2g"][I[p] - 1] for p in range(P)]  # :560-561
+        J = [trial_dofs[p]["l2g"][J[p] - 1] for p in range(P)]
+        cols = [setup_prange_with_ghosts(trial_dofs[p], J[p]) for p in range(P)]  # :564
+    else:
+        I = [test_dofs[p]["l2g"][I[p] - 1] for p in range(P)]  # :600-601
+        J = [trial_dofs[p]["l2g"][J[p] - 1] for p in range(P)]
+        rows = [setup_prange_with_ghosts(test_dofs[p], I[p]) for p in range(P)]  # :604
+        Jo = [trial_dofs[p]["l2o"][g2l(trial_dofs[p], J[p]) - 1] for p in range(P)]  # :608
+        I, J, Jo, V = assemble_coo_with_column_owner(I, J, V, rows, Jo)  # :609
+        b = None
+        if b_fe is not None:
+            brows = [prange_from_touched(test_dofs[p], touched[p]) for p in range(P)]  # :615
+            b = [rhs_callback(b_fe[p], test_dofs[p], brows[p]) for p in range(P)]  # :616
+        cols = [setup_prange_with_ghosts(trial_dofs[p], J[p], Jo[p]) for p in range(P)]  # :623
+        if b is not None:
+            b = assemble_pvector(b, brows)  # :626
+    out = []
+    for p in range(P):
+        li = g2l(rows[p], I[p])  # :629-630 / :567-568
+        lj = g2l(cols[p], J[p])
+        csr = coo_to_csr(li, lj, V[p], len(rows[p]["l2g"]), len(cols[p]["l2g"]))  # :636 / :574
+        out.append(dict(rows=rows[p], cols=cols[p], csr=csr, b=None if b is None else b[p],
+                        brows=None if (b is None or strategy == "fully") else brows[p]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# A14  mul!  ([ext] PartitionedArrays mul!) and consistent!
+# ------------------------------------------------------------------------------------------------
+
+
+def consistent(x_all, cols_all):
+    """owner -> ghost overwrite of a vector laid out on ``cols``."""
+    owner_val = {}
+    for x, c in zip(x_all, cols_all):
+        nown = len(c["own_to_local"])
+        owner_val.update(zip(c["l2g"][:nown].tolist(), x[:nown].tolist()))
+    for x, c in zip(x_all, cols_all):
+        nown = len(c["own_to_local"])
+        x[nown:] = [owner_val[g] for g in c["l2g"][nown:].tolist()]
+    return x_all
+
+
+def mul(parts, x_all, alpha=1.0, beta=0.0, y_all=None):
+    """y_own <- beta*y_own + alpha*(A_oo x_own + A_og x_ghost); only owned rows are produced."""
+    x_all = consistent([x.copy() for x in x_all], [p["cols"] for p in parts])
+    out = []
+    for k, (p, x) in enumerate(zip(parts, x_all)):
+        rowptr, colind, val = p["csr"]
+        nown = len(p["rows"]["own_to_local"])
+        y = np.zeros(nown)
+        prod = val * x[colind]
+        rid = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+        keep = rid < nown
+        np.add.at(y, rid[keep], prod[keep])
+        y0 = np.zeros(nown) if (y_all is None or beta == 0.0) else beta * y_all[k][:nown]
+        out.append(y0 + alpha * y)
+    return out

@@ -1,0 +1,131 @@
+"""Shared test drivers: build a distributed problem with the host mirror, run the CPU oracle on it."""
+import numpy as np
+import scipy.sparse as sp
+
+import graft_import
+from oracle import assembly_oracle as orc
+
+g = graft_import.load()
+
+
+class Problem:
+    pass
+
+
+def build_problem(parts, cells, order=2, tags="boundary", ufun=None, strategy="sub", domain=None, ncomp=1, backend=None):
+    pr = Problem()
+    D = len(parts)
+    pr.backend = backend or g.DebugBackend(int(np.prod(parts)))
+    pr.domain = domain if domain is not None else sum(([0.0, 1.0] for _ in cells), [])
+    pr.model = g.CartesianDiscreteModel(pr.backend, parts, pr.domain, cells)
+    pr.reffe = g.ReferenceFE("lagrangian", float, order, ncomp=ncomp)
+    pr.V = g.TestFESpace(pr.model, pr.reffe, dirichlet_tags=tags)
+    pr.U = g.TrialFESpace(ufun, pr.V)
+    pr.strategy = strategy
+    pr.trian = g.Triangulation(g.FullyAssembledRows(), pr.model) if strategy == "fully" else g.Triangulation(pr.model)
+    pr.D, pr.order, pr.ncomp = D, order, ncomp
+    return pr
+
+
+def cell_coords(model_local, cell_lids):
+    xyz = model_local.vertex_coordinates()
+    cv = model_local.cell_vertex_ids()[cell_lids - 1]
+    return xyz[cv - 1]
+
+
+def oracle_dofs(pr):
+    return [orc.local_indices(i.n_global, i.part, i.l2g, i.l2o) for i in pr.U.gids.indices]
+
+
+def oracle_assemble(pr, form=("poisson",), source=None, quad_degree=None, extra_cellvec=None, perturb=None):
+    """Run the oracle on every part.  Returns (per-part results, per-part (K,F) cell arrays)."""
+    qd = quad_degree or 2 * pr.order
+    I, J, V, B, T, KF = [], [], [], [], [], []
+    dofs = oracle_dofs(pr)
+    for k, (m, s) in enumerate(zip(pr.model.models, pr.U.spaces)):
+        lids = pr.trian.cell_lids[k]
+        X = cell_coords(m, lids)
+        if perturb is not None:
+            X = perturb(m, lids, X)
+        K, F = orc.integrate_cells(form, X, s.ref_nodes, pr.order, pr.ncomp, qd, source)
+        ids = s.cell_dof_ids[lids - 1]
+        F = orc.lift_dirichlet(K, F, ids, pr.U.dirichlet_values[k])
+        if extra_cellvec is not None:
+            F = F + extra_cellvec[k]
+        mask = (dofs[k]["l2o"] != dofs[k]["part"]) if pr.strategy == "fully" else None
+        i, j, v, b, t = orc.numeric_loop(ids, ids, K, F, s.num_free_dofs, mask)
+        I.append(i); J.append(j); V.append(v); B.append(b); T.append(t); KF.append((K, F))
+    out = orc.create_from_nz(pr.strategy, I, J, V, B, T, dofs, dofs)
+    return out, KF
+
+
+def gather_global(out):
+    """Global scipy CSR + rhs from the owned rows of every part (what `\\` gathers, README.md:76)."""
+    n = out[0]["rows"]["n"]
+    rows, cols, vals = [], [], []
+    b = np.zeros(n)
+    for p in out:
+        rowptr, colind, val = p["csr"]
+        nown = len(p["rows"]["own_to_local"])
+        rid = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+        keep = rid < nown
+        rows.append(p["rows"]["l2g"][rid[keep]] - 1)
+        cols.append(p["cols"]["l2g"][colind[keep]] - 1)
+        vals.append(val[keep])
+        if p["b"] is not None:
+            b[p["rows"]["l2g"][:nown] - 1] += p["b"][:nown]
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    return A, b
+
+
+def l2_error(pr, xglob, ufun, quad_degree=None):
+    """sqrt(sum ∫ |u-uh|^2 dΩ) over owned cells (reference test/PoissonTests.jl:43-45)."""
+    qd = quad_degree or 2 * pr.order
+    tot = 0.0
+    for k, (m, s, ids) in enumerate(zip(pr.model.models, pr.U.spaces, pr.U.gids.indices)):
+        own = pr.model.cell_gids.indices[k].own_to_local
+        X = cell_coords(m, own)
+        phi, dphi, w, xi = orc.reference_tables(pr.D, pr.order, s.ref_nodes, qd)
+        N, dN = orc.geometry_tables(pr.D, xi)
+        cd = s.cell_dof_ids[own - 1]
+        free = xglob[ids.l2g[np.maximum(cd, 1) - 1] - 1]
+        dv = pr.U.dirichlet_values[k]
+        dirv = dv[np.clip(-cd, 1, max(len(dv), 1)) - 1] if len(dv) else np.zeros(cd.shape)
+        uc = np.where(cd > 0, free, dirv)
+        uh = np.einsum("qi,ci->cq", phi, uc)
+        xq = np.einsum("qv,cvd->dcq", N, X)
+        ue = ufun(xq.reshape(pr.D, -1)).reshape(uh.shape)
+        J = np.einsum("cvd,qva->cqda", X, dN)
+        tot += float(np.einsum("q,cq,cq->", w, np.abs(np.linalg.det(J)), (ue - uh) ** 2))
+    return np.sqrt(tot)
+
+
+def neumann_cellvec_2d(pr, gfun, tags=(6, 8), quad_degree=4):
+    """∫ v g dΓ on the boundary facets of the integrated cells whose Cartesian entity is in ``tags``
+    (2-D: 6 = top, 8 = right; reference test/PoissonTests.jl:19-23,39).  Returned per parent cell."""
+    x1, w1 = orc.gauss_legendre_01((quad_degree + 2) // 2)
+    out = []
+    for k, (m, s) in enumerate(zip(pr.model.models, pr.U.spaces)):
+        lids = pr.trian.cell_lids[k]
+        X = cell_coords(m, lids)
+        ci = m.cell_multi_index()[lids - 1] + m.cmin[None, :]
+        F = np.zeros((len(lids), s.nd))
+        for tag, (axis, side) in {5: (1, 0), 6: (1, 1), 7: (0, 0), 8: (0, 1)}.items():
+            if tag not in tags:
+                continue
+            sel = np.flatnonzero(ci[:, axis] == (m.ncells_global[axis] - 1 if side else 0))
+            if len(sel) == 0:
+                continue
+            other = 1 - axis
+            xi = np.zeros((len(x1), 2)); xi[:, axis] = side; xi[:, other] = x1
+            val = [orc.lagrange_1d(pr.order, xi[:, d])[0] for d in range(2)]
+            tix = np.rint(s.ref_nodes * pr.order).astype(int)
+            phi = val[0][:, tix[:, 0]] * val[1][:, tix[:, 1]]
+            N, _ = orc.geometry_tables(2, xi)
+            xq = np.einsum("qv,cvd->dcq", N, X[sel])
+            length = np.abs(X[sel][:, -1, other] - X[sel][:, 0, other])
+            normal = np.zeros(2); normal[axis] = 1.0 if side else -1.0
+            gq = gfun(xq.reshape(2, -1), normal).reshape(len(sel), -1)
+            F[sel] += np.einsum("q,c,qi,cq->ci", w1, length, phi, gq)
+        out.append(F)
+    return out

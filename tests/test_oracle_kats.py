@@ -1,0 +1,100 @@
+"""Pin the CPU oracle with every known-answer test the reference holds for the path."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from helpers import build_problem, gather_global, l2_error, neumann_cellvec_2d, oracle_assemble
+from oracle import assembly_oracle as orc
+
+
+def test_1d_q2_element_matrices():
+    # SURVEY 8c analytic KAT: Gridap node order (left, right, mid)
+    h = 0.7
+    X = np.array([[[0.0], [h]]])
+    ref = np.array([[0.0], [1.0], [0.5]])
+    K, _ = orc.integrate_cells(("poisson",), X, ref, 2, 1, 4)
+    M, _ = orc.integrate_cells(("mass",), X, ref, 2, 1, 4)
+    assert np.allclose(K[0], np.array([[7, 1, -8], [1, 7, -8], [-8, -8, 16]]) / (3 * h), rtol=1e-13)
+    assert np.allclose(M[0], np.array([[4, -1, 2], [-1, 4, 2], [2, 2, 16]]) * h / 30, rtol=1e-13)
+
+
+def test_3d_cartesian_cell_matrix_is_kronecker_sum():
+    from helpers import g
+    hx, hy, hz = 0.5, 0.25, 2.0
+    poly = g.NCube(3)
+    ref = poly.q2_ref_nodes()
+    X = (poly.vertex_coords * np.array([hx, hy, hz]))[None].astype(float)
+    K, _ = orc.integrate_cells(("poisson",), X, ref, 2, 1, 4)
+    k1 = lambda h: np.array([[7, -8, 1], [-8, 16, -8], [1, -8, 7]]) / (3 * h)  # tensor order (0, 1/2, 1)
+    m1 = lambda h: np.array([[4, 2, -1], [2, 16, 2], [-1, 2, 4]]) * h / 30
+    tix = np.rint(ref * 2).astype(int)
+    Kx, Ky, Kz, Mx, My, Mz = k1(hx), k1(hy), k1(hz), m1(hx), m1(hy), m1(hz)
+    a, b, c = tix[:, 0], tix[:, 1], tix[:, 2]
+    ref_K = (Kx[np.ix_(a, a)] * My[np.ix_(b, b)] * Mz[np.ix_(c, c)] + Mx[np.ix_(a, a)] * Ky[np.ix_(b, b)] * Mz[np.ix_(c, c)]
+             + Mx[np.ix_(a, a)] * My[np.ix_(b, b)] * Kz[np.ix_(c, c)])
+    assert np.allclose(K[0], ref_K, rtol=1e-12, atol=1e-14)
+    assert np.abs(K[0].sum(1)).max() < 1e-12  # row sums of the unconstrained Laplacian vanish
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+def test_poisson_config1_solution(strategy):
+    # reference test/PoissonTests.jl:14-45: 4x4 cells on (0,4)^2, (2,2) parts, Q2, u=(x+y)^2
+    u = lambda x: (x[0] + x[1]) ** 2
+    pr = build_problem((2, 2), (4, 4), 2, [1, 2, 3, 5, 7], u, strategy, domain=[0, 4, 0, 4])
+    assert sum(i.own_length for i in pr.U.gids.indices) == 64
+    gN = lambda x, n: 2 * (x[0] + x[1]) * (n[0] + n[1])
+    out, _ = oracle_assemble(pr, ("poisson",), source=-4.0, extra_cellvec=neumann_cellvec_2d(pr, gN))
+    for p in out:  # test/FESpacesTests.jl:29-31
+        assert len(p["csr"][0]) - 1 == len(p["rows"]["l2g"])
+        assert p["csr"][1].max() < len(p["cols"]["l2g"])
+    A, b = gather_global(out)
+    x = spla.spsolve(A.tocsc(), b)
+    assert l2_error(pr, x, u) < 1e-9
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+@pytest.mark.parametrize("parts", [(2, 2), (1, 1), (2, 1)])
+def test_rhs_sum_equals_length(strategy, parts):
+    # reference test/FESpacesTests.jl:61-70,174-181: l = ∫ 1*v, Q1, h=1, Dirichlet "boundary":
+    # every free (interior) node integrates to exactly 1
+    pr = build_problem(parts, (4, 4), 1, "boundary", None, strategy, domain=[0, 4, 0, 4])
+    out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+    _, b = gather_global(out)
+    assert len(b) == 9 and abs(b.sum() - len(b)) < 1e-12
+
+
+def test_fully_equals_sub_3d():
+    u = lambda x: x[0] + 2 * x[1] - x[2]
+    res = {}
+    for st in ("sub", "fully"):
+        pr = build_problem((2, 2, 2), (4, 4, 4), 2, "boundary", u, st)
+        out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+        res[st] = gather_global(out)
+    dA = abs(res["sub"][0] - res["fully"][0]).max()
+    assert dA < 1e-12 and np.abs(res["sub"][1] - res["fully"][1]).max() < 1e-12
+
+
+def test_nnz_closed_forms_single_part():
+    # nnz = (8N-9)^D, COO count = (9N-10)^D for Q2 with full Dirichlet boundary
+    N = 4
+    pr = build_problem((1, 1, 1), (N, N, N), 2, "boundary", None, "sub")
+    out, KF = oracle_assemble(pr)
+    assert len(out[0]["csr"][1]) == (8 * N - 9) ** 3
+    ids = pr.U.spaces[0].cell_dof_ids
+    assert int(((ids > 0).sum(1) ** 2).sum()) == (9 * N - 10) ** 3
+
+
+def test_mul_alpha_beta():
+    # reference test/BlockPartitionedArraysTests.jl:70-77: y <- alpha*(A x) + beta*y
+    pr = build_problem((2, 2), (6, 6), 2, "boundary", None, "sub")
+    out, _ = oracle_assemble(pr)
+    A, _ = gather_global(out)
+    rng = np.random.default_rng(0)
+    xg = rng.uniform(-1, 1, A.shape[0])
+    xs = [xg[p["cols"]["l2g"] - 1] for p in out]
+    ys = [rng.uniform(-1, 1, len(p["rows"]["l2g"])) for p in out]
+    yo = orc.mul(out, xs, 2.0, -0.5, ys)
+    for p, y, y0 in zip(out, yo, ys):
+        nown = len(p["rows"]["own_to_local"])
+        ref = 2.0 * (A @ xg)[p["rows"]["l2g"][:nown] - 1] - 0.5 * y0[:nown]
+        assert np.allclose(y, ref, rtol=1e-13, atol=1e-13)
