@@ -1,0 +1,110 @@
+"""ctypes binding of ``lib/libgraft.so`` (include/graft.h) -- the same C ABI the Julia shim binds with
+``ccall`` (julia/GraftAssembly.jl).  There is NO fallback: if the shared library is
+missing, or no CUDA device is present, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libgraft.so")
+
+c_i32, c_i64, c_dbl, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+P = C.POINTER
+
+# name -> argtypes (restype is int32 unless listed in _RESTYPES).  Keep in sync with include/graft.h;
+# tests/test_abi.py checks that every prototype in the header appears here and is exported.
+SIGNATURES = {
+    "graft_comm_create_local": [c_i32, P(c_vp)],
+    "graft_nccl_unique_id": [c_vp],
+    "graft_comm_create_nccl": [c_i32, c_i32, c_vp, c_i32, P(c_vp)],
+    "graft_comm_destroy": [c_vp],
+    "graft_ctx_create": [c_vp, c_i32, c_i32, P(c_vp)],
+    "graft_ctx_destroy": [c_vp],
+    "graft_last_error": [],
+    "graft_mesh_set_cartesian": [c_vp, c_i32, c_vp, c_vp, c_vp],
+    "graft_mesh_set_hex": [c_vp, c_i32, c_i64, c_vp, c_i64, c_vp],
+    "graft_mesh_update_coords": [c_vp, c_i64, c_vp],
+    "graft_space_set": [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp],
+    "graft_space_set_dirichlet_values": [c_vp, c_i32, c_i64, c_vp],
+    "graft_cells_set": [c_vp, c_i64, c_vp],
+    "graft_form_set": [c_vp, c_i32, c_vp, c_i32, c_i32],
+    "graft_source_set": [c_vp, c_i32, c_i32, c_vp, c_vp],
+    "graft_extra_cellvec_set": [c_vp, c_i32, c_vp],
+    "graft_symbolic": [c_vp, c_i32, c_i32],
+    "graft_prange_query": [c_vp, c_i32, c_i32, P(c_i64), P(c_i64), P(c_i64)],
+    "graft_prange_get": [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
+    "graft_csr_query": [c_vp, c_i32, c_i32, P(c_i64), P(c_i64), P(c_i64)],
+    "graft_csr_get": [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
+    "graft_csr_get_values": [c_vp, c_i32, c_i32, c_vp],
+    "graft_csr_device": [c_vp, c_i32, c_i32, P(c_vp), P(c_vp), P(c_vp)],
+    "graft_numeric": [c_vp, c_i32],
+    "graft_scatter_cellmats": [c_vp, c_i32, c_i32, c_vp, c_vp],
+    "graft_cellmats_get": [c_vp, c_i32, c_i32, c_vp, c_vp],
+    "graft_vec_get": [c_vp, c_i32, c_vp],
+    "graft_vec_device": [c_vp, c_i32, P(c_vp)],
+    "graft_spmv": [c_vp, c_i32, c_i32, c_dbl, c_vp, c_dbl, c_vp],
+    "graft_spmv_device": [c_vp, c_i32, c_i32, c_dbl, c_vp, c_dbl, c_vp],
+    "graft_timers_get": [c_vp, c_vp],
+    "graft_stats_get": [c_vp, c_vp],
+    "graft_sync": [c_vp],
+    "graft_version": [],
+}
+_RESTYPES = {"graft_last_error": C.c_char_p}
+
+T_SYMBOLIC, T_INTEGRATE, T_SCATTER, T_EXCHANGE, T_NUMERIC, T_SPMV, T_COUNT = 0, 1, 2, 3, 4, 5, 8
+FORM_POISSON, FORM_MASS, FORM_ELASTICITY, FORM_STOKES = 1, 2, 3, 4
+SOURCE_NONE, SOURCE_CONST, SOURCE_NODAL = 0, 1, 2
+
+
+class GraftError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen lib/libgraft.so and declare the prototypes.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GraftError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, c_i32)
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise GraftError(load().graft_last_error().decode())
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_vp)
+
+
+def ptr_array(ptrs):
+    """``T* const*`` from a list of numpy arrays / integer device addresses / None."""
+    arr = (c_vp * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        if p is None:
+            arr[i] = None
+        elif isinstance(p, np.ndarray):
+            arr[i] = p.ctypes.data
+        else:
+            arr[i] = int(p)
+    return arr

@@ -1,0 +1,41 @@
+"""GPU parity of mul! (halo-exchanged SpMV) against the oracle and a gathered global product."""
+import numpy as np
+import pytest
+
+from gpu_helpers import build_problem, graft_assemble, oracle_assemble
+from helpers import g, gather_global
+from oracle import assembly_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+@pytest.mark.parametrize("parts,cells", [((1, 1), (6, 6)), ((2, 2), (6, 6)), ((2, 2, 2), (4, 4, 4)), ((3, 1), (7, 4))])
+def test_mul_alpha_beta(parts, cells, strategy):
+    # reference test/BlockPartitionedArraysTests.jl:70-77: y <- alpha*(A x) + beta*y
+    pr = build_problem(parts, cells, 2, "boundary", None, strategy)
+    out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+    Ag, _ = gather_global(out)
+    assem, f, A, b = graft_assemble(pr, "poisson", source=1.0)
+    rng = np.random.default_rng(0)
+    xg = rng.uniform(-1, 1, Ag.shape[0])
+    x = g.pvector_on_cols(A, xg)
+    y = g.pvector_on_rows(A)
+    y0 = []
+    for v in y.vector_partition:
+        v[:] = rng.uniform(-1, 1, len(v)); y0.append(v.copy())
+    g.mul(y, A, x, 2.0, -0.5)
+    for k, (ids, cids) in enumerate(zip(A.row_partition.indices, A.col_partition.indices)):
+        no = ids.own_length
+        ref = 2.0 * (Ag @ xg)[ids.l2g[:no] - 1] - 0.5 * y0[k][:no]
+        assert np.allclose(y.vector_partition[k][:no], ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+        # consistent!(x): ghost entries now hold the owners' values
+        assert np.array_equal(x.vector_partition[k], xg[cids.l2g - 1])
+    # beta = 0 must ignore (even NaN) content of y, like mul!(y,A,x)
+    for v in y.vector_partition:
+        v[:] = np.nan
+    g.mul(y, A, x)
+    yo = orc.mul(out, [xg[p["cols"]["l2g"] - 1] for p in out])
+    for k, ids in enumerate(A.row_partition.indices):
+        assert np.allclose(y.vector_partition[k][: ids.own_length], yo[k], rtol=1e-12, atol=1e-12 * np.abs(yo[k]).max())
+    assem.close()
