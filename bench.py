@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement: matrix+vector assembly of 3-D Poisson Q2 on a hex mesh.
+
+A "step" is one pass of the hot path over one batch of synthetic input: one numeric (re)assembly
+(cell integration + Dirichlet lifting + deterministic scatter + ghost-row reduction) of the whole
+mesh.  N=1: BASELINE.json configs[1] (128^3 cells, one part).  N=2/4/8: parts (2,1,1)/(2,2,1)/(2,2,2),
+128^3 OWNED cells per part (weak scaling; N=8 is configs[2], 256^3 cells), one part per GPU, NCCL
+ghost-row reduction.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells C] [--geometry cartesian|hex]
+
+Prints ONE JSON line (rank 0).  `value` = assembled nnz/s with inputs resident in HBM; `e2e` = the same
+through the C ABI with HOST buffers (pinned): per step the Dirichlet values and the source term go
+host->device and the assembled CSR values + right-hand side come back device->host.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/) on the host cores
+(the Julia reference cannot run in this image: no julia, no MPI).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+METRIC = "assembled nnz/s (3D Poisson Q2 hex, FP64 matrix+vector assembly)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); out["sm_max_mhz"] = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def algorithmic_bytes(nnz, nrows, nd, ncells, D, nnodes_geom):
+    """values written once, rhs written once, cell_dof_ids read once, coordinates read once."""
+    return 8 * nnz + 8 * nrows + 4 * nd * ncells + 8 * D * nnodes_geom
+
+
+def cpu_reference_run(cells, steps, warmup):
+    """The oracle (numpy restatement of the reference algorithm, A1-A12) on ONE part, `cells`^3 cells."""
+    from helpers import build_problem, oracle_assemble
+
+    pr = build_problem((1, 1, 1), (cells,) * 3, 2, "boundary", lambda x: x[0] + x[1] + x[2], "sub")
+    times, nnz = [], 0
+    for it in range(warmup + steps):
+        t = time.perf_counter()
+        out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+        dt = time.perf_counter() - t
+        nnz = len(out[0]["csr"][1])
+        if it >= warmup:
+            times.append(dt)
+    return dict(ncells=cells**3, nnz=nnz, seconds=float(np.mean(times)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = args.ref_cells
+    r = cpu_reference_run(c, args.steps, min(args.warmup, 1))
+    v = r["nnz"] / r["seconds"]
+    sample = f"{c}^3 cells single part (same form/space/quadrature), numpy oracle incl. COO materialisation + COO->CSR"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D Poisson Q2 hex, {c}^3 cells, 1 part (bounded sample of the 128^3 workload)", "cells_per_s": r["ncells"] / r["seconds"]},
+            "cpu_baseline": {"value": v, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft")
+    ap.add_argument("--cells", type=int, default=128, help="owned cells per direction per part")
+    ap.add_argument("--ref-cells", type=int, default=16)
+    ap.add_argument("--geometry", default="cartesian", choices=["cartesian", "hex"])
+    ap.add_argument("--strategy", default="sub", choices=["sub", "fully"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--spmv-steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import graft_import
+
+    g = graft_import.load()
+    L = g.libgraft
+    from helpers import build_problem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        backend = g.DistBackend()
+    else:
+        backend = g.DebugBackend(1)
+    parts = PARTS[args.gpus]
+    cells = tuple(p * args.cells for p in parts)
+    t0 = time.time()
+    u = lambda x: x[0] + x[1] + x[2]
+    pr = build_problem(parts, cells, 2, "boundary", u, args.strategy, backend=backend)
+    t_setup = time.time() - t0
+    strategy = g.FullyAssembledRows() if args.strategy == "fully" else g.SubAssembledRows()
+    assem = g.SparseMatrixAssembler(pr.U, pr.V, strategy, geometry=args.geometry, device=local_rank)
+    dΩ = g.Measure(pr.trian, 4)
+    form = g.Poisson(dΩ, source=1.0)
+    lib, comm, ctx = assem.comm.lib, assem.comm.handle, assem.comm.ctxs[0]
+    assem._set_form(form)
+    t0 = time.time()
+    assem._symbolic(form)
+    t_symbolic_wall = time.time() - t0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n, what=3):
+        for _ in range(n):
+            L.check(lib.graft_numeric(comm, what))
+        L.check(lib.graft_sync(comm))
+
+    # ---- device-resident numeric assembly ---------------------------------------------------------
+    run_steps(args.warmup)
+    st0 = assem.stats()[0]
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    per_step = []
+    for _ in range(args.steps):
+        L.check(lib.graft_numeric(comm, 3))
+        L.check(lib.graft_sync(comm))
+        per_step.append(assem.timers()[0][L.T_NUMERIC])  # CUDA events on the library's own streams
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    st1 = assem.stats()[0]
+    dev_ms = float(np.sum(per_step))
+    tim = assem.timers()[0]
+    # max over ranks of the device time
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(t[0]), float(t[1])
+        cnt = torch.tensor([st1["nnz"], st1["ncells"], 0], device="cuda", dtype=torch.int64)
+        # count only OWNED rows' nnz / owned cells for the aggregate
+        m = A_own_nnz(assem, L, lib, ctx)
+        cnt[0] = m
+        cnt[1] = len(pr.model.cell_gids.indices[0].own_to_local)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        tot_nnz, tot_cells = int(cnt[0]), int(cnt[1])
+    else:
+        wall_ms = wall * 1e3
+        tot_nnz, tot_cells = st1["nnz"], st1["ncells"]
+    ms_per_step = dev_ms / args.steps
+    value = tot_nnz / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (per part)
+    sp = pr.U.spaces[0]
+    m_loc = pr.model.models[0]
+    nnodes_geom = int(np.prod(m_loc.ncells_local + 1))
+    B_num = algorithmic_bytes(st1["nnz"], st1["nrows"], sp.nd, st1["ncells"], 3, nnodes_geom)
+    peak, peak_src = measured_peak()
+    kern_ms = float(np.mean(per_step))  # fused route: one kernel is the step
+    dominant = "fused_rows_kernel" if st1["path"] == "fused-affine" else "integrate_cells_kernel+scatter_rows_kernel"
+    achieved = B_num / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": dominant, "algorithmic_bytes_per_launch": B_num, "peak_source": peak_src,
+                "phase_ms": {"integrate": float(tim[L.T_INTEGRATE]), "scatter": float(tim[L.T_SCATTER]), "exchange": float(tim[L.T_EXCHANGE])}}
+
+    # ---- SpMV (mul!) device-resident ---------------------------------------------------------------
+    spmv = None
+    try:
+        n_cols = st1["ncols"]; n_own = assem.rows[0].indices[0].own_length
+        x = torch.ones(n_cols, dtype=torch.float64, device="cuda")
+        y = torch.zeros(max(n_own, 1), dtype=torch.float64, device="cuda")
+        xs, ys = L.ptr_array([x.data_ptr()]), L.ptr_array([y.data_ptr()])
+        for _ in range(3):
+            L.check(lib.graft_spmv_device(comm, 0, 0, 1.0, xs, 0.0, ys))
+        L.check(lib.graft_sync(comm)); barrier()
+        ts = []
+        for _ in range(args.spmv_steps):
+            L.check(lib.graft_spmv_device(comm, 0, 0, 1.0, xs, 0.0, ys))
+            L.check(lib.graft_sync(comm))
+            ts.append(assem.timers()[0][L.T_SPMV])
+        barrier()
+        sp_ms = float(np.mean(ts))
+        if dist is not None:
+            t = torch.tensor([sp_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); sp_ms = float(t[0])
+        B_spmv = 12 * st1["nnz"] + 4 * (st1["nrows"] + 1) + 8 * st1["nrows"] + 8 * st1["ncols"]
+        spmv = {"ms": sp_ms, "GBps": B_spmv / (sp_ms * 1e-3) / 1e9, "frac_of_peak": B_spmv / (sp_ms * 1e-3) / 1e9 / peak,
+                "algorithmic_bytes": B_spmv}
+    except Exception as e:  # pragma: no cover
+        spmv = {"error": str(e)}
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nnz, nrows = st1["nnz"], st1["nrows"]
+        dv = torch.from_numpy(np.ascontiguousarray(pr.U.dirichlet_values[0])).pin_memory()
+        src = torch.ones(1, dtype=torch.float64).pin_memory()
+        vals = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        bh = torch.empty(nrows, dtype=torch.float64).pin_memory()
+        vp, bp, dvp, srp = vals.numpy(), bh.numpy(), dv.numpy(), src.numpy()
+
+        def e2e_step():
+            if len(dvp):
+                L.check(lib.graft_space_set_dirichlet_values(ctx, 0, len(dvp), L.ptr(dvp)))
+            L.check(lib.graft_source_set(ctx, 0, L.SOURCE_CONST, L.ptr(srp), None))
+            L.check(lib.graft_numeric(comm, 3))
+            L.check(lib.graft_csr_get_values(ctx, 0, 0, L.ptr(vp)))
+            L.check(lib.graft_vec_get(ctx, 0, L.ptr(bp)))
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t[0])
+        e2e = {"value": tot_nnz * e2e_steps / dt, "unit": "nnz/s", "h2d_bytes_per_step": int(8 * len(dvp) + 8),
+               "d2h_bytes_per_step": int(8 * nnz + 8 * nrows), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "checksum": float(vp[: min(nnz, 1 << 20)].sum())}
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.ref_cells, 2, 1)
+        cpu = {"value": r["nnz"] / r["seconds"], "unit": "nnz/s", "cores": 1, "kind": "port",
+               "sample": f"{args.ref_cells}^3-cell single-part sample of the same workload, numpy oracle (COO materialisation + COO->CSR), {r['seconds']:.2f} s/step",
+               "cells_per_s": r["ncells"] / r["seconds"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"3D Poisson Q2 hex, {'x'.join(str(c) for c in cells)} cells, parts {parts}, {args.strategy}-assembled rows, "
+                                       f"geometry={args.geometry}, re-assembly (numeric phase) of matrix+vector",
+                           "cells": tot_cells, "nnz": tot_nnz, "cells_per_s": tot_cells / (ms_per_step * 1e-3), "route": st1["path"],
+                           "l2": "inputs+outputs (>9 GB per step) exceed the 126 MB L2; no explicit flush",
+                           "symbolic_ms_device": float(tim[L.T_SYMBOLIC]), "symbolic_s_wall": t_symbolic_wall, "host_setup_s": t_setup,
+                           "wall_ms_per_step": wall_ms / args.steps},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "spmv": spmv,
+                "gpu_launches": int(st1["launches"] - st0["launches"]), "clocks": clocks}
+        print(json.dumps(line))
+    assem.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def A_own_nnz(assem, L, lib, ctx):
+    """nnz of the owned rows of this part (ghost rows are structural zeros owned elsewhere)."""
+    import ctypes as C
+
+    m, n, nnz = L.c_i64(), L.c_i64(), L.c_i64()
+    L.check(lib.graft_csr_query(ctx, 0, 0, C.byref(m), C.byref(n), C.byref(nnz)))
+    rowptr = np.empty(m.value + 1, dtype=np.int64)
+    L.check(lib.graft_csr_get(ctx, 0, 0, L.ptr(rowptr), None, None))
+    return int(rowptr[assem.rows[0].indices[0].own_length] - assem.index_base)
+
+
+if __name__ == "__main__":
+    main()

@@ -67,7 +67,7 @@ struct DevBuf {
     if (count > 0) CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)count * sizeof(T), s));
   }
   void upload(const T* h, int64_t count, cudaStream_t s) {
-    alloc(count);
+    if (count != n) alloc(count);  // reuse the allocation on repeated calls (cudaFree would synchronise)
     if (count > 0) CUDA_CHECK(cudaMemcpyAsync(p, h, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, s));
   }
   void download(T* h, cudaStream_t s) const {
@@ -158,7 +158,9 @@ struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
   DevBuf<int32_t> gstart;       // per own row: offset (from rowptr[r]) of the first ghost column
   DevBuf<int32_t> brow_list;    // own rows that have ghost columns
   int64_t n_brow = 0;
-  DevBuf<uint16_t> pos;         // per (entry, lj): offset inside the row, 0xFFFF = skipped column
+  DevBuf<uint16_t> pos;         // per (entry, lj): offset inside the row, 0xFFFF = skipped column (rows of >= 255 nnz)
+  DevBuf<uint8_t> pos8;         // same, 1 byte (0xFF = skipped) when every row has < 255 nnz: halves the map traffic
+  DevBuf<double> cellC;         // fused tier 2: per-cell coefficients of this block
   DevBuf<double> cellmats;      // ncells x nd_i x nd_j (unfused route / hook 1)
   DevBuf<double> cellvecs;      // ncells x nd_i (only block (bi,bi) carries the vector of field bi)
   // ghost-row value exchange plan (SubAssembledRows; assemble!(A))
@@ -212,8 +214,8 @@ struct graft_ctx {
   DevBuf<double> d_tab;  // packed reference tables
   // scratch for halo'd vectors in graft_spmv (host-buffer variant)
   DevBuf<double> x_dev, y_dev;
-  DevBuf<double> cellG;  // per integrated cell: affine geometry factors
-  DevBuf<int32_t> affine_flag;
+  DevBuf<double> cellJinv, celldet;  // per integrated cell: constant inverse Jacobian and |det J| (affine cells)
+  bool geom_valid = false;
 };
 
 // ------------------------------------------------------------------------------------------------

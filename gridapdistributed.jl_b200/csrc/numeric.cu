@@ -17,12 +17,13 @@
 struct ScatterArgs {
   int64_t m;
   const int64_t* rowptr; const int64_t* rc_ptr; const int32_t* rc_list;
-  const uint16_t* pos; const double* cellmats; int nd_j; int maxrowlen;
+  const void* pos; const double* cellmats; int nd_j; int maxrowlen;
   double* vals;
   // vector (NULL: skip)
   const double* cellvecs; double* b;
 };
 
+template <typename PosT>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a) {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -37,10 +38,10 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a) {
       for (int64_t t = t0; t < t1; ++t) {
         int64_t e = a.rc_list[t];
         const double* src = a.cellmats + e * a.nd_j;
-        const uint16_t* pp = a.pos + t * a.nd_j;
+        const PosT* pp = (const PosT*)a.pos + t * a.nd_j;
         for (int lj = lane; lj < a.nd_j; lj += 32) {
-          uint16_t p = pp[lj];
-          if (p != 0xffffu) acc[p] += src[lj];  // distinct lj -> distinct columns: no conflict inside a warp step
+          PosT p = pp[lj];
+          if (p != (PosT)~(PosT)0) acc[p] += src[lj];  // distinct lj -> distinct columns: no conflict inside a warp step
         }
         __syncwarp();
       }
@@ -87,16 +88,21 @@ static void launch_scatter(graft_ctx* x, int bi, int bj, const double* cellmats,
   if (B.m <= 0) return;
   ScatterArgs a{};
   a.m = B.m; a.rowptr = B.rowptr.p; a.rc_ptr = ri.rc_ptr.p; a.rc_list = ri.rc_list.p;
-  a.pos = B.pos.p; a.cellmats = cellmats; a.nd_j = cj.nd; a.maxrowlen = std::max(B.maxrowlen, 1);
+  a.pos = B.pos8.n ? (const void*)B.pos8.p : (const void*)B.pos.p; a.cellmats = cellmats; a.nd_j = cj.nd; a.maxrowlen = std::max(B.maxrowlen, 1);
   a.vals = with_mat ? B.vals.p : nullptr;
   a.cellvecs = with_vec ? cellvecs : nullptr;
   a.b = with_vec ? ri.b.p : nullptr;
   int wpb = 8;
   size_t smem = (size_t)wpb * a.maxrowlen * sizeof(double);
   while (smem > 160 * 1024 && wpb > 1) { wpb >>= 1; smem = (size_t)wpb * a.maxrowlen * sizeof(double); }
-  if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = std::min<int64_t>(cdiv(B.m, wpb), (int64_t)148 * 32);
-  scatter_rows_kernel<<<(unsigned)grid, wpb * 32, smem, x->stream>>>(a);
+  if (B.pos8.n) {
+    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(scatter_rows_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scatter_rows_kernel<uint8_t><<<(unsigned)grid, wpb * 32, smem, x->stream>>>(a);
+  } else {
+    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(scatter_rows_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scatter_rows_kernel<uint16_t><<<(unsigned)grid, wpb * 32, smem, x->stream>>>(a);
+  }
   CUDA_CHECK(cudaGetLastError());
   x->launches += 1;
 }

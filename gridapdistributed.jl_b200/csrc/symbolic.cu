@@ -162,6 +162,7 @@ struct RowUniqueArgs {
   const int64_t* rowptr;          // fill mode (indexed by row - row_begin)
   int32_t* colind;
   uint16_t* pos;                  // [(entry index t) * nd_j + lj]; may be NULL
+  uint8_t* pos8;                  // 1-byte variant (exactly one of pos / pos8 is used)
   int32_t* gstart;                // may be NULL
   int cap;                        // power of two, uint32 slots per warp
 };
@@ -245,7 +246,7 @@ __global__ void row_unique_kernel(RowUniqueArgs a) {
         }
         a.gstart[r - a.row_begin] = lo;
       }
-      if (a.pos) {
+      if (a.pos || a.pos8) {
         for (int64_t t = t0; t < t1; ++t) {
           int e = a.rc_list[t];
           int64_t k = e / a.nd_i;
@@ -264,7 +265,8 @@ __global__ void row_unique_kernel(RowUniqueArgs a) {
                 p = (uint16_t)lo;
               }
             }
-            a.pos[t * a.nd_j + lj] = p;
+            if (a.pos8) a.pos8[t * a.nd_j + lj] = (p == 0xffffu) ? (uint8_t)0xff : (uint8_t)p;
+            else a.pos[t * a.nd_j + lj] = p;
           }
         }
       }
@@ -291,6 +293,16 @@ __global__ void max_i32_kernel(const int32_t* __restrict__ a, int64_t n, int* __
   if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
+// exact number of COO triplets the reference would allocate (nz_counter, Algebra.jl:410-418)
+__global__ void count_coo_kernel(const int32_t* __restrict__ eids_r, const int32_t* __restrict__ eids_c, int64_t nc, int nd_r, int nd_c,
+                                 const int32_t* __restrict__ rowmap, unsigned long long* __restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nc) return;
+  int nr = 0, ncol = 0;
+  for (int l = 0; l < nd_r; ++l) { int id = eids_r[k * nd_r + l]; nr += (id > 0 && rowmap[id - 1] >= 0); }
+  for (int l = 0; l < nd_c; ++l) ncol += eids_c[k * nd_c + l] > 0;
+  if (nr * ncol) atomicAdd(out, (unsigned long long)(nr * ncol));
+}
 // rows with ghost columns (boundary rows of the SpMV)
 __global__ void brow_flag_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ gstart, int64_t n_own_rows,
                                  int32_t* __restrict__ flag) {
@@ -781,7 +793,7 @@ void symbolic_phase(graft_comm* c, int strategy, int index_base) {
           exclusive_scan_i32_to_i64(rowlen.p, S.gptr.p, ng + 1, s, &S.npairs);
           CUDA_CHECK(cudaStreamSynchronize(s));
           S.gcol_felid.alloc(S.npairs);
-          a.rowlen = nullptr; a.rowptr = S.gptr.p; a.colind = S.gcol_felid.p; a.pos = nullptr; a.gstart = nullptr;
+          a.rowlen = nullptr; a.rowptr = S.gptr.p; a.colind = S.gcol_felid.p; a.pos = nullptr; a.pos8 = nullptr; a.gstart = nullptr;
           launch_row_unique<true>(x, a);
           S.gi.alloc(S.npairs); S.gj.alloc(S.npairs); S.prow.alloc(S.npairs);
           if (ng > 0)
@@ -950,9 +962,18 @@ void symbolic_phase(graft_comm* c, int strategy, int index_base) {
         B.colind.alloc(B.nnz);
         B.vals.alloc_zero(B.nnz, s);
         B.gstart.alloc(m);
-        B.pos.alloc(ri.nentries * cj.nd);
-        B.ncoo = 0;
-        a.rowlen = nullptr; a.rowptr = B.rowptr.p; a.colind = B.colind.p; a.pos = B.pos.p; a.gstart = B.gstart.p;
+        B.pos.release(); B.pos8.release();
+        if (B.maxrowlen < 255) B.pos8.alloc(ri.nentries * cj.nd); else B.pos.alloc(ri.nentries * cj.nd);
+        {
+          DevBuf<unsigned long long> cc;
+          cc.alloc_zero(1, s);
+          count_coo_kernel<<<nblk(x->ncells_int), 256, 0, s>>>(ri.eids.p, cj.eids.p, x->ncells_int, ri.nd, cj.nd, ri.rows.map.p, cc.p);
+          unsigned long long hc = 0;
+          CUDA_CHECK(cudaMemcpyAsync(&hc, cc.p, 8, cudaMemcpyDeviceToHost, s));
+          CUDA_CHECK(cudaStreamSynchronize(s));
+          B.ncoo = (int64_t)hc;
+        }
+        a.rowlen = nullptr; a.rowptr = B.rowptr.p; a.colind = B.colind.p; a.pos = B.pos.p; a.pos8 = B.pos8.p; a.gstart = B.gstart.p;
         launch_row_unique<true>(x, a);
         CUDA_CHECK(cudaMemcpyAsync(&B.ghost_nnz_begin, B.rowptr.p + n_own, 8, cudaMemcpyDeviceToHost, s));
         // boundary rows of the SpMV

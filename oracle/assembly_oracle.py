@@ -98,7 +98,8 @@ def integrate_cells(form, cell_coords, ref_nodes, order, ncomp, quad_degree, sou
     """Cell matrices K[c,i,j] (test i = row, trial j = col) and vectors f[c,i] by quadrature (A.4).
 
     form: ("poisson",) | ("mass",) | ("elasticity", lam, mu).  cell_coords: (ncells, 2^D, D).
-    source: None | float | callable f(x[D,npts]) -> [npts] (scalar) or [ncomp,npts].
+    source: None | float | callable f(x[D,npts]) -> [npts] (scalar) or [ncomp,npts] | ndarray (ncells, nd) of
+    nodal values of an FE-function source.
     """
     ncells, nv, D = cell_coords.shape
     phi, dphi, w, xi = reference_tables(D, order, ref_nodes, quad_degree)
@@ -137,7 +138,11 @@ def integrate_cells(form, cell_coords, ref_nodes, order, ncomp, quad_degree, sou
             for c in range(ncomp):  # componentwise scalar forms
                 K[s : s + chunk, c * nds : (c + 1) * nds, c * nds : (c + 1) * nds] = Ks
         if source is not None:
-            if callable(source):
+            if isinstance(source, np.ndarray):
+                # FE-function source: nodal values per cell dof (ncells, nd); f(x_q) = sum_k phi_k(xi_q) F_k
+                Fn = source[s : s + chunk].reshape(len(X), ncomp, nds)
+                fq = np.einsum("qk,cak->acq", phi, Fn)
+            elif callable(source):
                 xq = np.einsum("qv,cvd->dcq", N, X).reshape(D, -1)
                 fq = np.asarray(source(xq), dtype=np.float64)
                 fq = fq.reshape(ncomp, len(X), -1) if fq.ndim == 2 else np.broadcast_to(fq.reshape(1, len(X), -1), (ncomp, len(X), len(w)))

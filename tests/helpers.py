@@ -47,7 +47,8 @@ def oracle_assemble(pr, form=("poisson",), source=None, quad_degree=None, extra_
         X = cell_coords(m, lids)
         if perturb is not None:
             X = perturb(m, lids, X)
-        K, F = orc.integrate_cells(form, X, s.ref_nodes, pr.order, pr.ncomp, qd, source)
+        src = source[1][k] if (isinstance(source, tuple) and source[0] == "nodal") else source
+        K, F = orc.integrate_cells(form, X, s.ref_nodes, pr.order, pr.ncomp, qd, src)
         ids = s.cell_dof_ids[lids - 1]
         F = orc.lift_dirichlet(K, F, ids, pr.U.dirichlet_values[k])
         if extra_cellvec is not None:
