@@ -101,6 +101,7 @@ int32_t graft_ctx_create(graft_comm* c, int32_t part, int32_t device, graft_ctx*
   x->comm = c;
   x->part = part;
   x->device = device;
+  CUDA_CHECK(cudaDeviceGetAttribute(&x->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->cstream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_a, cudaEventDisableTiming));

@@ -131,8 +131,12 @@ struct Space {
   // row structures of this field as a block-row (symbolic phase)
   PRangeDev rows, cols, brows;
   DevBuf<int64_t> rc_ptr;   // local rows + 1: row -> its (cell,li) entries, ascending cell order
-  DevBuf<int32_t> rc_list;  // entry = k*nd + li   (k = position in the integrated-cell list)
+  DevBuf<int32_t> rc_list;  // entry = k*nd + li   (k = position in the integrated-cell list); symbolic phase only
   int64_t nentries = 0;
+  // the same lists padded to chunks of 4 entries per row (-1 = padding): what the numeric kernels read
+  DevBuf<int64_t> ck_ptr;   // local rows + 1: row -> first chunk
+  DevBuf<int32_t> rc_pad;   // 4 * nchunks entries
+  int64_t nchunks = 0;
   DevBuf<double> b;         // right-hand side on `brows`
   // vector exchange plan (assemble!(b): ghost -> owner, +)
   std::vector<int> vsnd_parts, vrcv_parts;
@@ -158,8 +162,12 @@ struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
   DevBuf<int32_t> gstart;       // per own row: offset (from rowptr[r]) of the first ghost column
   DevBuf<int32_t> brow_list;    // own rows that have ghost columns
   int64_t n_brow = 0;
-  DevBuf<uint16_t> pos;         // per (entry, lj): offset inside the row, 0xFFFF = skipped column (rows of >= 255 nnz)
-  DevBuf<uint8_t> pos8;         // same, 1 byte (0xFF = skipped) when every row has < 255 nnz: halves the map traffic
+  // scatter map: for every (chunk of 4 entries, local col dof lj) the offsets of the 4 columns inside
+  // the row, packed in one 32-bit word (1 byte each, 0xFF = skipped column) when every row has
+  // < 255 nnz, else in two words (2 bytes each, 0xFFFF = skipped): posw[(chunk*nd_j + lj)*pos_bytes ...]
+  DevBuf<uint32_t> posw;
+  int pos_bytes = 1;
+  DevBuf<int32_t> rowrec;       // 4 x int32 per row: {rowptr lo, rowptr hi, first chunk, len | nentries << 16}
   DevBuf<double> cellC;         // fused tier 2: per-cell coefficients of this block
   DevBuf<double> cellmats;      // ncells x nd_i x nd_j (unfused route / hook 1)
   DevBuf<double> cellvecs;      // ncells x nd_i (only block (bi,bi) carries the vector of field bi)
@@ -193,7 +201,7 @@ struct CommBase;
 
 struct graft_ctx {
   graft_comm* comm = nullptr;
-  int part = 1, device = 0;
+  int part = 1, device = 0, num_sms = 148;
   cudaStream_t stream = nullptr, cstream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
   cudaEvent_t tev[8] = {nullptr};  // timing events: numeric start / integrate / scatter / exchange, spmv start / end

@@ -16,14 +16,13 @@
 // one warp per row; the row's values are accumulated in shared memory and stored once, coalesced
 struct ScatterArgs {
   int64_t m;
-  const int64_t* rowptr; const int64_t* rc_ptr; const int32_t* rc_list;
-  const void* pos; const double* cellmats; int nd_j; int maxrowlen;
+  const int64_t* rowptr; const int64_t* ck_ptr; const int32_t* rc_pad;
+  const uint32_t* posw; int pos_bytes; const double* cellmats; int nd_j; int maxrowlen;
   double* vals;
   // vector (NULL: skip)
   const double* cellvecs; double* b;
 };
 
-template <typename PosT>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a) {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -31,28 +30,37 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a) {
   for (int64_t r = (int64_t)blockIdx.x * wpb + warp; r < a.m; r += (int64_t)gridDim.x * wpb) {
     int64_t o = a.rowptr[r];
     int len = (int)(a.rowptr[r + 1] - o);
-    int64_t t0 = a.rc_ptr[r], t1 = a.rc_ptr[r + 1];
+    int64_t c0 = a.ck_ptr[r], c1 = a.ck_ptr[r + 1];
     if (a.vals) {
       for (int i = lane; i < len; i += 32) acc[i] = 0.0;
       __syncwarp();
-      for (int64_t t = t0; t < t1; ++t) {
-        int64_t e = a.rc_list[t];
-        const double* src = a.cellmats + e * a.nd_j;
-        const PosT* pp = (const PosT*)a.pos + t * a.nd_j;
-        for (int lj = lane; lj < a.nd_j; lj += 32) {
-          PosT p = pp[lj];
-          if (p != (PosT)~(PosT)0) acc[p] += src[lj];  // distinct lj -> distinct columns: no conflict inside a warp step
+    }
+    double bsum = 0.0;
+    for (int64_t c = c0; c < c1; ++c) {
+      int4 e4 = *reinterpret_cast<const int4*>(a.rc_pad + 4 * c);
+      int es[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt) {
+        if (es[tt] < 0) break;
+        int64_t e = es[tt] & 0x0fffffff;
+        if (a.vals) {
+          const double* src = a.cellmats + e * a.nd_j;
+          for (int lj = lane; lj < a.nd_j; lj += 32) {
+            uint32_t p, skip;
+            if (a.pos_bytes == 1) { p = (a.posw[c * a.nd_j + lj] >> (8 * tt)) & 0xffu; skip = 0xffu; }
+            else { p = (a.posw[(c * a.nd_j + lj) * 2 + (tt >> 1)] >> (16 * (tt & 1))) & 0xffffu; skip = 0xffffu; }
+            if (p != skip) acc[p] += src[lj];  // distinct lj -> distinct columns: no conflict inside a warp step
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        if (a.b) bsum += a.cellvecs[e];  // b[i] += f[li] in cell order (Algebra.jl:811-821)
       }
+    }
+    if (a.vals) {
       for (int i = lane; i < len; i += 32) a.vals[o + i] = acc[i];
       __syncwarp();
     }
-    if (a.b && lane == 0) {
-      double s = 0.0;
-      for (int64_t t = t0; t < t1; ++t) s += a.cellvecs[a.rc_list[t]];  // b[i] += f[li] in cell order (Algebra.jl:811-821)
-      a.b[r] = s;
-    }
+    if (a.b && lane == 0) a.b[r] = bsum;
   }
 }
 
@@ -87,22 +95,17 @@ static void launch_scatter(graft_ctx* x, int bi, int bj, const double* cellmats,
   Space& cj = x->fields[bj];
   if (B.m <= 0) return;
   ScatterArgs a{};
-  a.m = B.m; a.rowptr = B.rowptr.p; a.rc_ptr = ri.rc_ptr.p; a.rc_list = ri.rc_list.p;
-  a.pos = B.pos8.n ? (const void*)B.pos8.p : (const void*)B.pos.p; a.cellmats = cellmats; a.nd_j = cj.nd; a.maxrowlen = std::max(B.maxrowlen, 1);
+  a.m = B.m; a.rowptr = B.rowptr.p; a.ck_ptr = ri.ck_ptr.p; a.rc_pad = ri.rc_pad.p;
+  a.posw = B.posw.p; a.pos_bytes = B.pos_bytes; a.cellmats = cellmats; a.nd_j = cj.nd; a.maxrowlen = std::max(B.maxrowlen, 1);
   a.vals = with_mat ? B.vals.p : nullptr;
   a.cellvecs = with_vec ? cellvecs : nullptr;
   a.b = with_vec ? ri.b.p : nullptr;
   int wpb = 8;
   size_t smem = (size_t)wpb * a.maxrowlen * sizeof(double);
   while (smem > 160 * 1024 && wpb > 1) { wpb >>= 1; smem = (size_t)wpb * a.maxrowlen * sizeof(double); }
-  int64_t grid = std::min<int64_t>(cdiv(B.m, wpb), (int64_t)148 * 32);
-  if (B.pos8.n) {
-    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(scatter_rows_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scatter_rows_kernel<uint8_t><<<(unsigned)grid, wpb * 32, smem, x->stream>>>(a);
-  } else {
-    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(scatter_rows_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scatter_rows_kernel<uint16_t><<<(unsigned)grid, wpb * 32, smem, x->stream>>>(a);
-  }
+  int64_t grid = std::min<int64_t>(cdiv(B.m, wpb), (int64_t)x->num_sms * 8);
+  if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scatter_rows_kernel<<<(unsigned)grid, wpb * 32, smem, x->stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   x->launches += 1;
 }

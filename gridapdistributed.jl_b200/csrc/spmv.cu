@@ -10,35 +10,79 @@
 // second matrix is stored.  HBM-bound: 12 B per nnz (8 B value + 4 B column id).
 #include "internal.h"
 
-template <int MODE>  // 0: interior (own columns, applies beta), 1: boundary rows (ghost columns, accumulates)
-__global__ void __launch_bounds__(256) spmv_rows_kernel(int64_t nrows, const int32_t* __restrict__ row_list, const int64_t* __restrict__ rowptr,
-                                                        const int32_t* __restrict__ gstart, const int32_t* __restrict__ colind,
-                                                        const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                                                        double alpha, double beta) {
+// Interior product: y_own = beta*y_own + alpha * A[:, own cols] x_own.  One warp owns RPW consecutive rows = one
+// contiguous nnz range, so that every lane has several independent 12-byte (value, column) loads in
+// flight; entries of ghost columns (col >= n_own_cols, the tail of each row) are masked here and
+// handled by the boundary kernel after the halo has arrived.
+template <int RPW>
+__global__ void __launch_bounds__(256) spmv_interior_kernel(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                                            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                                                            int n_own_cols, double alpha, double beta) {
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ngroups = (nrows + RPW - 1) / RPW;
+  for (; w < ngroups; w += nw) {
+    const int64_t r0 = w * RPW;
+    int64_t myp = 0;
+    if (lane <= RPW) { int64_t rr = r0 + lane; myp = rowptr[rr < nrows ? rr : nrows]; }
+    int64_t p[RPW + 1];
+#pragma unroll
+    for (int j = 0; j <= RPW; ++j) p[j] = __shfl_sync(0xffffffffu, myp, j);
+    double sum[RPW];
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) sum[j] = 0.0;
+    int64_t t = p[0] + lane;
+    const int64_t end = p[RPW];
+    for (; t + 96 < end; t += 128) {
+      double v[4]; int c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { v[u] = __ldcs(vals + t + 32 * u); c[u] = __ldcs(colind + t + 32 * u); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        double prod = c[u] < n_own_cols ? v[u] * x[c[u]] : 0.0;
+        int64_t tt = t + 32 * u;
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) sum[j] += (tt >= p[j] && tt < p[j + 1]) ? prod : 0.0;
+      }
+    }
+    for (; t < end; t += 32) {
+      double vv = __ldcs(vals + t); int cc = __ldcs(colind + t);
+      double prod = cc < n_own_cols ? vv * x[cc] : 0.0;
+#pragma unroll
+      for (int j = 0; j < RPW; ++j) sum[j] += (t >= p[j] && t < p[j + 1]) ? prod : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], o);
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) mine = lane == j ? sum[j] : mine;
+    if (lane < RPW && r0 + lane < nrows) {
+      int64_t rr = r0 + lane;
+      y[rr] = (beta == 0.0) ? alpha * mine : beta * y[rr] + alpha * mine;
+    }
+  }
+}
+
+// Boundary rows: y[r] += alpha * sum over the ghost columns of row r (the tail [rowptr[r]+gstart[r], rowptr[r+1])).
+__global__ void __launch_bounds__(256) spmv_boundary_kernel(int64_t nrows, const int32_t* __restrict__ row_list, const int64_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ gstart, const int32_t* __restrict__ colind,
+                                                            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                                                            double alpha) {
   const int lane = threadIdx.x & 31;
   int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (; w < nrows; w += nw) {
-    int64_t r = MODE == 0 ? w : (int64_t)row_list[w];
-    int64_t s = rowptr[r], e = rowptr[r + 1];
-    int64_t mid = s + gstart[r];
-    int64_t t0 = MODE == 0 ? s : mid, t1 = MODE == 0 ? mid : e;
+    int64_t r = (int64_t)row_list[w];
+    int64_t t0 = rowptr[r] + gstart[r], t1 = rowptr[r + 1];
     double sum = 0.0;
-    int64_t t = t0 + lane;
-    // two independent loads in flight per lane
-    for (; t + 32 < t1; t += 64) {
-      double v0 = vals[t], v1 = vals[t + 32];
-      int c0 = colind[t], c1 = colind[t + 32];
-      sum += v0 * x[c0];
-      sum += v1 * x[c1];
-    }
-    if (t < t1) sum += vals[t] * x[colind[t]];
+    for (int64_t t = t0 + lane; t < t1; t += 32) sum += vals[t] * x[colind[t]];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) {
-      if (MODE == 0) y[r] = (beta == 0.0) ? alpha * sum : beta * y[r] + alpha * sum;
-      else y[r] += alpha * sum;
-    }
+    if (lane == 0) y[r] += alpha * sum;
   }
 }
 
@@ -119,17 +163,18 @@ void spmv_phase(graft_comm* c, int bi, int bj, double alpha, double* const* xs, 
     Space& ri = x->fields[bi];
     int64_t n_own = ri.rows.n_own;
     if (n_own > 0) {
-      int64_t grid = std::min<int64_t>(cdiv(n_own * 32, 256), (int64_t)148 * 64);
-      spmv_rows_kernel<0><<<(unsigned)grid, 256, 0, x->stream>>>(n_own, nullptr, B.rowptr.p, B.gstart.p, B.colind.p, B.vals.p, dx[k], dy[k],
-                                                                  alpha, beta);
+      const int RPW = 4;
+      int64_t grid = std::min<int64_t>(cdiv(cdiv(n_own, RPW) * 32, 256), (int64_t)x->num_sms * 8);
+      spmv_interior_kernel<RPW><<<(unsigned)grid, 256, 0, x->stream>>>(n_own, B.rowptr.p, B.colind.p, B.vals.p, dx[k], dy[k],
+                                                                       (int)x->fields[bj].cols.n_own, alpha, beta);
       x->launches += 1;
     }
     if (multi) {
       CUDA_CHECK(cudaStreamWaitEvent(x->stream, x->ev_b, 0));
       if (B.n_brow > 0) {
-        int64_t grid = std::min<int64_t>(cdiv(B.n_brow * 32, 256), (int64_t)148 * 64);
-        spmv_rows_kernel<1><<<(unsigned)grid, 256, 0, x->stream>>>(B.n_brow, B.brow_list.p, B.rowptr.p, B.gstart.p, B.colind.p, B.vals.p,
-                                                                    dx[k], dy[k], alpha, beta);
+        int64_t grid = std::min<int64_t>(cdiv(B.n_brow * 32, 256), (int64_t)x->num_sms * 8);
+        spmv_boundary_kernel<<<(unsigned)grid, 256, 0, x->stream>>>(B.n_brow, B.brow_list.p, B.rowptr.p, B.gstart.p, B.colind.p, B.vals.p,
+                                                                     dx[k], dy[k], alpha);
         x->launches += 1;
       }
     }
