@@ -135,8 +135,9 @@ struct Space {
   int64_t nentries = 0;
   // the same lists padded to chunks of 4 entries per row (-1 = padding): what the numeric kernels read
   DevBuf<int64_t> ck_ptr;   // local rows + 1: row -> first chunk
-  DevBuf<int32_t> rc_pad;   // 4 * nchunks entries
+  DevBuf<int32_t> rc_pad;   // 4 * nchunks entries (symbolic phase only)
   int64_t nchunks = 0;
+  DevBuf<int32_t> ent;      // numeric kernels: per entry, position of the cell in the integrated-cell list | Dirichlet flags << 28
   DevBuf<double> b;         // right-hand side on `brows`
   // vector exchange plan (assemble!(b): ghost -> owner, +)
   std::vector<int> vsnd_parts, vrcv_parts;
@@ -150,6 +151,20 @@ struct Space {
   DevBuf<int32_t> hsnd_idx;  // own col index to pack, grouped by destination
   DevBuf<int32_t> hrcv_idx;  // ghost index (0-based within ghosts) of every received value
   DevBuf<double> hsnd_buf, hrcv_buf;
+};
+
+// Pattern classes of the rows of a block (gather.cu): rows with the same local topology share one
+// contribution list; rows are processed in batches of one class.
+struct RowClasses {
+  int64_t nclasses = 0, nbatches = 0, nplanes = 0;
+  int max_nent = 0;
+  DevBuf<uint32_t> srow;       // sorted position -> row (rows of a class are contiguous, ascending)
+  DevBuf<int32_t> cls_first;   // nclasses + 1: first sorted position of every class
+  DevBuf<int32_t> cls;         // int4 per class: {len, nent, first chunk (index into ccp), first li (index into cls_li)}
+  DevBuf<int64_t> ccp;         // per (class, chunk of 32 nnz slots): first plane; total chunks + 1
+  DevBuf<uint32_t> planes;     // 32 words per plane: (t*nd_j + lj) << 16 | (li*nd_j + lj)
+  DevBuf<int32_t> cls_li;      // local row dof of every entry of every class
+  DevBuf<int32_t> batch;       // int4 per batch: {class, first sorted position, rows, 0}
 };
 
 struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
@@ -167,7 +182,7 @@ struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
   // < 255 nnz, else in two words (2 bytes each, 0xFFFF = skipped): posw[(chunk*nd_j + lj)*pos_bytes ...]
   DevBuf<uint32_t> posw;
   int pos_bytes = 1;
-  DevBuf<int32_t> rowrec;       // 4 x int32 per row: {rowptr lo, rowptr hi, first chunk, len | nentries << 16}
+  RowClasses rc;
   DevBuf<double> cellC;         // fused tier 2: per-cell coefficients of this block
   DevBuf<double> cellmats;      // ncells x nd_i x nd_j (unfused route / hook 1)
   DevBuf<double> cellvecs;      // ncells x nd_i (only block (bi,bi) carries the vector of field bi)
@@ -263,6 +278,32 @@ void exclusive_scan_i32_to_i64(const int32_t* d_in, int64_t* d_out, int64_t n, c
 void radix_sort_pairs_u32(uint32_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits, cudaStream_t s, graft_ctx* ctx);
 void radix_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, int64_t n, int key_bits, cudaStream_t s, graft_ctx* ctx);
 
+// arguments of the numeric gather kernels (gather.cu); filled by the affine host code (fused.cu)
+struct GatherArgs {
+  // row classes
+  int64_t nbatches;
+  const int4* batch; const int4* cls; const uint32_t* srow; const int64_t* ccp; const uint32_t* planes; const int32_t* cls_li;
+  const int64_t* rowptr; const int64_t* ent_ptr; const int32_t* ent;
+  int nd_i, nd_j, nds_i, nds_j, ncomp_i, ncomp_j, nS;
+  int ks, kstride;          // T2 / MAT per-warp buffer: doubles per entry, doubles per row
+  int tlen;                 // T1: doubles of the per-warp row template
+  const double* tab;        // T1: Kbar[nd_i][nd_j] ; T2: S[nS][nds_i][nds_j]
+  const double* cellC;      // T2: [cell][ncomp_i][ncomp_j][nS]
+  const double* cellmats;   // MAT: [cell][nd_i][nd_j]
+  double* vals;             // NULL: skip the matrix
+  // vector part (b == NULL: skip)
+  double* b; int b_accumulate;  // 0: b = source + extra - lift ; 1: b -= lift (later block of a block row)
+  const int32_t* eids_j; const double* dirvals_j; int dirbit;
+  int src_kind; double src_const[3];
+  const double* msum;       // [nds_i]: sum_q w phi_i
+  const double* M;          // [nds_i][nds_i] reference mass matrix (nodal source)
+  const double* celldet;    // T2: |det J| per cell
+  double det_uniform;       // T1
+  const int32_t* eids_i; const double* src_free; const double* src_dir;
+  const double* extra;      // [cell][nd_i] or NULL
+  const double* cellvecs;   // MAT: lifted cell vectors [cell][nd_i]
+};
+
 // ------------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------------
@@ -270,6 +311,10 @@ void symbolic_phase(graft_comm* c, int strategy, int index_base);           // s
 void numeric_phase(graft_comm* c, int what);                                // numeric.cu
 void scatter_user_cellmats(graft_comm* c, int bi, int bj, const double* const* mats, const double* const* vecs);
 void integrate_cells_unfused(graft_ctx* ctx, int what);                     // integrate.cu
+void build_entry_words(graft_ctx* x, int f, const uint32_t* cellflags);     // gather.cu
+void build_row_classes(graft_ctx* x, int bi, int bj);                       // gather.cu
+void gather_scatter_mat(graft_ctx* x, int bi, int bj, const double* cellmats, const double* cellvecs, bool with_mat, bool with_vec);
+void gather_fill_and_launch_affine(graft_ctx* x, int bi, int bj, int tier, GatherArgs& a, int ntab, bool vec);
 bool fused_affine_available(graft_ctx* ctx);                                // fused.cu
 void numeric_fused_affine(graft_ctx* ctx, int what);                        // fused.cu
 void spmv_phase(graft_comm* c, int bi, int bj, double alpha, double* const* x, double beta, double* const* y, bool on_device);  // spmv.cu

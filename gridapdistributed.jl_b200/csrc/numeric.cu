@@ -8,61 +8,10 @@
 //   COO -> CSR duplicate sum          Gridap sparse_from_coo -> sparsecsr [ext]
 //   value part of assemble_coo_with_column_owner! / assemble!(A)   Algebra.jl:1048-1131, 530-535
 //   _rhs_callback + assemble!(b)      Algebra.jl:720-753, 786-789, 898-907
-// No floating-point atomics anywhere: every nnz is summed by ONE warp in a fixed order (ascending
-// cell position = the reference's triplet order after its stable sort), so re-assembly is bitwise
-// repeatable.  Ghost-row values received from neighbours are added in ascending neighbour order.
+// The gather kernels themselves are in gather.cu.  No floating-point atomics anywhere: every nnz is
+// summed by ONE lane in a fixed order (ascending cell position = the reference's triplet order after
+// its stable sort), so re-assembly is bitwise repeatable.  Ghost-row values received from neighbours are added in ascending neighbour order.
 #include "internal.h"
-
-// one warp per row; the row's values are accumulated in shared memory and stored once, coalesced
-struct ScatterArgs {
-  int64_t m;
-  const int64_t* rowptr; const int64_t* ck_ptr; const int32_t* rc_pad;
-  const uint32_t* posw; int pos_bytes; const double* cellmats; int nd_j; int maxrowlen;
-  double* vals;
-  // vector (NULL: skip)
-  const double* cellvecs; double* b;
-};
-
-__global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a) {
-  extern __shared__ double sacc[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  double* acc = sacc + (size_t)warp * a.maxrowlen;
-  for (int64_t r = (int64_t)blockIdx.x * wpb + warp; r < a.m; r += (int64_t)gridDim.x * wpb) {
-    int64_t o = a.rowptr[r];
-    int len = (int)(a.rowptr[r + 1] - o);
-    int64_t c0 = a.ck_ptr[r], c1 = a.ck_ptr[r + 1];
-    if (a.vals) {
-      for (int i = lane; i < len; i += 32) acc[i] = 0.0;
-      __syncwarp();
-    }
-    double bsum = 0.0;
-    for (int64_t c = c0; c < c1; ++c) {
-      int4 e4 = *reinterpret_cast<const int4*>(a.rc_pad + 4 * c);
-      int es[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-      for (int tt = 0; tt < 4; ++tt) {
-        if (es[tt] < 0) break;
-        int64_t e = es[tt] & 0x0fffffff;
-        if (a.vals) {
-          const double* src = a.cellmats + e * a.nd_j;
-          for (int lj = lane; lj < a.nd_j; lj += 32) {
-            uint32_t p, skip;
-            if (a.pos_bytes == 1) { p = (a.posw[c * a.nd_j + lj] >> (8 * tt)) & 0xffu; skip = 0xffu; }
-            else { p = (a.posw[(c * a.nd_j + lj) * 2 + (tt >> 1)] >> (16 * (tt & 1))) & 0xffffu; skip = 0xffffu; }
-            if (p != skip) acc[p] += src[lj];  // distinct lj -> distinct columns: no conflict inside a warp step
-          }
-          __syncwarp();
-        }
-        if (a.b) bsum += a.cellvecs[e];  // b[i] += f[li] in cell order (Algebra.jl:811-821)
-      }
-    }
-    if (a.vals) {
-      for (int i = lane; i < len; i += 32) a.vals[o + i] = acc[i];
-      __syncwarp();
-    }
-    if (a.b && lane == 0) a.b[r] = bsum;
-  }
-}
 
 __global__ void pack_i64_kernel(const double* __restrict__ vals, const int64_t* __restrict__ idx, int64_t n, double* __restrict__ buf) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,24 +39,7 @@ __global__ void zero_f64_kernel(double* p, int64_t n) {
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)std::max<int64_t>(1, cdiv(n, t)); }
 
 static void launch_scatter(graft_ctx* x, int bi, int bj, const double* cellmats, const double* cellvecs, bool with_mat, bool with_vec) {
-  Block& B = x->blocks[bi][bj];
-  Space& ri = x->fields[bi];
-  Space& cj = x->fields[bj];
-  if (B.m <= 0) return;
-  ScatterArgs a{};
-  a.m = B.m; a.rowptr = B.rowptr.p; a.ck_ptr = ri.ck_ptr.p; a.rc_pad = ri.rc_pad.p;
-  a.posw = B.posw.p; a.pos_bytes = B.pos_bytes; a.cellmats = cellmats; a.nd_j = cj.nd; a.maxrowlen = std::max(B.maxrowlen, 1);
-  a.vals = with_mat ? B.vals.p : nullptr;
-  a.cellvecs = with_vec ? cellvecs : nullptr;
-  a.b = with_vec ? ri.b.p : nullptr;
-  int wpb = 8;
-  size_t smem = (size_t)wpb * a.maxrowlen * sizeof(double);
-  while (smem > 160 * 1024 && wpb > 1) { wpb >>= 1; smem = (size_t)wpb * a.maxrowlen * sizeof(double); }
-  int64_t grid = std::min<int64_t>(cdiv(B.m, wpb), (int64_t)x->num_sms * 8);
-  if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  scatter_rows_kernel<<<(unsigned)grid, wpb * 32, smem, x->stream>>>(a);
-  CUDA_CHECK(cudaGetLastError());
-  x->launches += 1;
+  gather_scatter_mat(x, bi, bj, cellmats, with_vec ? cellvecs : nullptr, with_mat, with_vec);
 }
 
 // ghost rows -> owners: matrix values (bit 0 of what) and vector values (bit 1)
