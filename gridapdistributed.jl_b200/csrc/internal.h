@@ -164,7 +164,16 @@ struct RowClasses {
   DevBuf<int64_t> ccp;         // per (class, chunk of 32 nnz slots): first plane; total chunks + 1
   DevBuf<uint32_t> planes;     // 32 words per plane: (t*nd_j + lj) << 16 | (li*nd_j + lj)
   DevBuf<int32_t> cls_li;      // local row dof of every entry of every class
-  DevBuf<int32_t> batch;       // int4 per batch: {class, first sorted position, rows, 0}
+  // batches of up to 8 rows of one class, ordered by first row
+  DevBuf<int32_t> brec;        // int4 per batch: {class, rows, len, nent}
+  DevBuf<uint32_t> brow;       // 8 per batch: row | needs-lifting flag << 31
+  DevBuf<int64_t> brp, bep;    // 8 per batch: rowptr[row], first entry of the row
+  // T1: values / right-hand side of a row of every class (recomputed by every numeric call)
+  int tlen = 0;
+  DevBuf<double> tmpl, cbsum;
+  DevBuf<uint32_t> rowclass;   // per row: class | needs-lifting flag << 31
+  DevBuf<int32_t> flagrows;    // the rows with the flag
+  int64_t nflagged = 0;
 };
 
 struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
@@ -281,9 +290,11 @@ void radix_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, int64_t n, int key
 // arguments of the numeric gather kernels (gather.cu); filled by the affine host code (fused.cu)
 struct GatherArgs {
   // row classes
-  int64_t nbatches;
-  const int4* batch; const int4* cls; const uint32_t* srow; const int64_t* ccp; const uint32_t* planes; const int32_t* cls_li;
-  const int64_t* rowptr; const int64_t* ent_ptr; const int32_t* ent;
+  int64_t nbatches, nclasses;
+  const int4* brec; const uint32_t* brow; const int64_t* brp; const int64_t* bep;
+  const int4* cls; const int64_t* ccp; const uint32_t* planes; const int32_t* cls_li; const int32_t* ent;
+  double* tmpl; double* cbsum;  // T1: per-class row values / right-hand side
+  int64_t m; const int64_t* rowptr; const uint32_t* rowclass; const int64_t* ent_ptr;  // T1 streams rows in row order
   int nd_i, nd_j, nds_i, nds_j, ncomp_i, ncomp_j, nS;
   int ks, kstride;          // T2 / MAT per-warp buffer: doubles per entry, doubles per row
   int tlen;                 // T1: doubles of the per-warp row template
