@@ -173,6 +173,12 @@ struct RowClasses {
   DevBuf<double> tmpl, cbsum;
   DevBuf<uint32_t> rowclass;   // per row: class | needs-lifting flag << 31
   DevBuf<int32_t> flagrows;    // the rows with the flag
+  // T2 tensor-core route: per class {offset lo, offset hi, k-steps, column tiles} and the tables in fragment order
+  int t_nS = 0;
+  int64_t t_nfrag = 0;
+  DevBuf<int32_t> tcls;
+  DevBuf<double> tfrag;
+  DevBuf<double> cls_fs;       // per class entry: constant-source factor (rebuilt by every numeric call)
   int64_t nflagged = 0;
 };
 
@@ -294,6 +300,7 @@ struct GatherArgs {
   const int4* brec; const uint32_t* brow; const int64_t* brp; const int64_t* bep;
   const int4* cls; const int64_t* ccp; const uint32_t* planes; const int32_t* cls_li; const int32_t* ent;
   double* tmpl; double* cbsum;  // T1: per-class row values / right-hand side
+  const int4* tcls; double* tfrag; const double* cls_fs;  // T2 tensor-core route: class tables
   int64_t m; const int64_t* rowptr; const uint32_t* rowclass; const int64_t* ent_ptr;  // T1 streams rows in row order
   int nd_i, nd_j, nds_i, nds_j, ncomp_i, ncomp_j, nS;
   int ks, kstride;          // T2 / MAT per-warp buffer: doubles per entry, doubles per row
