@@ -10,60 +10,39 @@
 // second matrix is stored.  HBM-bound: 12 B per nnz (8 B value + 4 B column id).
 #include "internal.h"
 
-// Interior product: y_own = beta*y_own + alpha * A[:, own cols] x_own.  One warp owns RPW consecutive rows = one
-// contiguous nnz range, so that every lane has several independent 12-byte (value, column) loads in
-// flight; entries of ghost columns (col >= n_own_cols, the tail of each row) are masked here and
-// handled by the boundary kernel after the halo has arrived.
-template <int RPW>
+// Interior product: y_own = beta*y_own + alpha * A[:, own cols] x_own.  Half a warp owns one row; every lane issues
+// up to 8 independent (value, column) loads before the first use (rows of Q2 hexes have 27..125 nnz: one pass),
+// so that each SM keeps > 40 KB in flight; entries of ghost columns (col >= n_own_cols, the tail of each row) are
+// masked here and handled by the boundary kernel after the halo has arrived.  The sum of a row is a fixed
+// xor-shuffle tree over 16 lanes: deterministic.
 __global__ void __launch_bounds__(256) spmv_interior_kernel(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                                                             const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
                                                             int n_own_cols, double alpha, double beta) {
-  const int lane = threadIdx.x & 31;
-  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t ngroups = (nrows + RPW - 1) / RPW;
-  for (; w < ngroups; w += nw) {
-    const int64_t r0 = w * RPW;
-    int64_t myp = 0;
-    if (lane <= RPW) { int64_t rr = r0 + lane; myp = rowptr[rr < nrows ? rr : nrows]; }
-    int64_t p[RPW + 1];
+  const int l16 = threadIdx.x & 15;
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int64_t nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  const int64_t nloop = (nrows + nhw - 1) / nhw;  // uniform trip count: the shuffles need the whole warp
+  for (int64_t it = 0; it < nloop; ++it, r += nhw) {
+    const bool rowok = r < nrows;
+    int64_t t0 = 0, t1 = 0;
+    if (rowok) { t0 = __ldg(rowptr + r); t1 = __ldg(rowptr + r + 1); }
+    double sum = 0.0;
+    for (int64_t t = t0 + l16; __any_sync(0xffffffffu, t < t1); t += 128) {
+      double v[8];
+      int c[8];
 #pragma unroll
-    for (int j = 0; j <= RPW; ++j) p[j] = __shfl_sync(0xffffffffu, myp, j);
-    double sum[RPW];
-#pragma unroll
-    for (int j = 0; j < RPW; ++j) sum[j] = 0.0;
-    int64_t t = p[0] + lane;
-    const int64_t end = p[RPW];
-    for (; t + 96 < end; t += 128) {
-      double v[4]; int c[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { v[u] = __ldcs(vals + t + 32 * u); c[u] = __ldcs(colind + t + 32 * u); }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        double prod = c[u] < n_own_cols ? v[u] * x[c[u]] : 0.0;
-        int64_t tt = t + 32 * u;
-#pragma unroll
-        for (int j = 0; j < RPW; ++j) sum[j] += (tt >= p[j] && tt < p[j + 1]) ? prod : 0.0;
+      for (int u = 0; u < 8; ++u) {
+        const bool on = t + 16 * u < t1;
+        v[u] = on ? __ldcs(vals + t + 16 * u) : 0.0;
+        c[u] = on ? __ldcs(colind + t + 16 * u) : n_own_cols;
       }
-    }
-    for (; t < end; t += 32) {
-      double vv = __ldcs(vals + t); int cc = __ldcs(colind + t);
-      double prod = cc < n_own_cols ? vv * x[cc] : 0.0;
 #pragma unroll
-      for (int j = 0; j < RPW; ++j) sum[j] += (t >= p[j] && t < p[j + 1]) ? prod : 0.0;
+      for (int u = 0; u < 8; ++u)
+        if (c[u] < n_own_cols) sum += v[u] * __ldg(x + c[u]);
     }
 #pragma unroll
-    for (int j = 0; j < RPW; ++j) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], o);
-    }
-    double mine = 0.0;
-#pragma unroll
-    for (int j = 0; j < RPW; ++j) mine = lane == j ? sum[j] : mine;
-    if (lane < RPW && r0 + lane < nrows) {
-      int64_t rr = r0 + lane;
-      y[rr] = (beta == 0.0) ? alpha * mine : beta * y[rr] + alpha * mine;
-    }
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (rowok && l16 == 0) y[r] = (beta == 0.0) ? alpha * sum : beta * y[r] + alpha * sum;
   }
 }
 
@@ -163,10 +142,9 @@ void spmv_phase(graft_comm* c, int bi, int bj, double alpha, double* const* xs, 
     Space& ri = x->fields[bi];
     int64_t n_own = ri.rows.n_own;
     if (n_own > 0) {
-      const int RPW = 4;
-      int64_t grid = std::min<int64_t>(cdiv(cdiv(n_own, RPW) * 32, 256), (int64_t)x->num_sms * 8);
-      spmv_interior_kernel<RPW><<<(unsigned)grid, 256, 0, x->stream>>>(n_own, B.rowptr.p, B.colind.p, B.vals.p, dx[k], dy[k],
-                                                                       (int)x->fields[bj].cols.n_own, alpha, beta);
+      int64_t grid = std::min<int64_t>(cdiv(n_own * 16, 256), (int64_t)x->num_sms * 8);
+      spmv_interior_kernel<<<(unsigned)grid, 256, 0, x->stream>>>(n_own, B.rowptr.p, B.colind.p, B.vals.p, dx[k], dy[k],
+                                                                  (int)x->fields[bj].cols.n_own, alpha, beta);
       x->launches += 1;
     }
     if (multi) {
