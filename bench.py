@@ -89,35 +89,61 @@ def algorithmic_bytes(nnz, nrows, nd, ncells, D, nnodes_geom):
     return 8 * nnz + 8 * nrows + 4 * nd * ncells + 8 * D * nnodes_geom
 
 
-def cpu_reference_run(cells, steps, warmup):
-    """The oracle (numpy restatement of the reference algorithm, A1-A12) on ONE part, `cells`^3 cells."""
-    from helpers import build_problem, oracle_assemble
+def host_parts(nthreads):
+    """Factor the host thread count into a 3-D part grid (x fastest gets the largest factor)."""
+    p, dims, d = nthreads, [1, 1, 1], 0
+    f = 2
+    while p > 1:
+        while p % f:
+            f += 1
+        dims[d % 3] *= f
+        p //= f
+        d += 1
+    return tuple(sorted(dims, reverse=True))
 
-    pr = build_problem((1, 1, 1), (cells,) * 3, 2, "boundary", lambda x: x[0] + x[1] + x[2], "sub")
+
+def cpu_reference_run(cells, steps, warmup, threads=None):
+    """The reference algorithm on the host cores: oracle/assembly_ref.c (per-cell quadrature, one COO triplet per
+    (cell,i,j), COO->CSR sort + duplicate sum), one OS thread per mesh part like one MPI rank per part in the
+    reference's with_mpi mode; `cells`^3 owned cells per part, P = host threads parts, no ghost exchange timed."""
+    from helpers import build_problem
+    from oracle import c_oracle
+
+    threads = threads or os.cpu_count() or 1
+    parts = host_parts(threads)
+    pr = build_problem(parts, tuple(p * cells for p in parts), 2, "boundary", lambda x: x[0] + x[1] + x[2], "sub")
+    inputs = [c_oracle.part_inputs(pr, k) for k in range(len(pr.model.models))]
     times, nnz = [], 0
     for it in range(warmup + steps):
         t = time.perf_counter()
-        out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+        res = c_oracle.assemble_poisson_q2(pr, source=1.0, threads=threads, keep=False, inputs=inputs)
         dt = time.perf_counter() - t
-        nnz = len(out[0]["csr"][1])
+        nnz = sum(r[1] for r in res)
         if it >= warmup:
             times.append(dt)
-    return dict(ncells=cells**3, nnz=nnz, seconds=float(np.mean(times)))
+    ncells = sum(len(i[2]) for i in inputs)
+    return dict(ncells=ncells, nnz=nnz, seconds=float(np.mean(times)), threads=threads, parts=parts, cells=cells)
+
+
+def cpu_sample_text(r):
+    return (f"{r['parts']} parts x {r['cells']}^3 owned cells (same form/space/quadrature as the 128^3 workload), C restatement of the "
+            f"reference algorithm (oracle/assembly_ref.c: per-cell quadrature, COO materialisation, COO->CSR), one thread per part, "
+            f"{r['seconds']:.2f} s/step")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    c = args.ref_cells
-    r = cpu_reference_run(c, args.steps, min(args.warmup, 1))
+    r = cpu_reference_run(args.ref_cells, args.steps, min(args.warmup, 1))
     v = r["nnz"] / r["seconds"]
-    sample = f"{c}^3 cells single part (same form/space/quadrature), numpy oracle incl. COO materialisation + COO->CSR"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D Poisson Q2 hex, {c}^3 cells, 1 part (bounded sample of the 128^3 workload)", "cells_per_s": r["ncells"] / r["seconds"]},
-            "cpu_baseline": {"value": v, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": sample},
+            "config": {"workload": f"3D Poisson Q2 hex, {r['parts']} parts x {r['cells']}^3 cells on {r['threads']} host threads "
+                                   f"(bounded sample of the 128^3-cells-per-GPU workload; the Julia reference cannot run in this image)",
+                       "cells_per_s": r["ncells"] / r["seconds"]},
+            "cpu_baseline": {"value": v, "unit": "nnz/s", "cores": r["threads"], "kind": "port", "sample": cpu_sample_text(r)},
             "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -129,7 +155,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft")
     ap.add_argument("--cells", type=int, default=128, help="owned cells per direction per part")
-    ap.add_argument("--ref-cells", type=int, default=16)
+    ap.add_argument("--ref-cells", type=int, default=32, help="CPU baseline: owned cells per direction per part (one part per host thread)")
+    ap.add_argument("--no-general", action="store_true", help="skip the extra measurement of the general (hex-node) route")
     ap.add_argument("--geometry", default="cartesian", choices=["cartesian", "hex"])
     ap.add_argument("--strategy", default="sub", choices=["sub", "fully"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,10 +257,19 @@ def main():
     B_num = algorithmic_bytes(st1["nnz"], st1["nrows"], sp.nd, st1["ncells"], 3, nnodes_geom)
     peak, peak_src = measured_peak()
     kern_ms = float(np.mean(per_step))  # fused route: one kernel is the step
-    dominant = "fused_rows_kernel" if st1["path"] == "fused-affine" else "integrate_cells_kernel+scatter_rows_kernel"
+    dominant = {("fused-affine", "cartesian"): "stream_t1_kernel", ("fused-affine", "hex"): "gemm_rows_kernel"}.get(
+        (st1["path"], args.geometry), "integrate_cells_kernel+gather_rows_kernel")
     achieved = B_num / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.cells == 128 and args.gpus == 1:
+            traffic = tj.get(dominant)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dominant, "algorithmic_bytes_per_launch": B_num, "peak_source": peak_src,
+                "note": "achieved = algorithmic bytes / device time of the whole numeric step (all kernels of the step, CUDA events on the library stream)",
                 "phase_ms": {"integrate": float(tim[L.T_INTEGRATE]), "scatter": float(tim[L.T_SCATTER]), "exchange": float(tim[L.T_EXCHANGE])}}
 
     # ---- SpMV (mul!) device-resident ---------------------------------------------------------------
@@ -260,6 +296,41 @@ def main():
                 "algorithmic_bytes": B_spmv}
     except Exception as e:  # pragma: no cover
         spmv = {"error": str(e)}
+
+    # ---- the other geometry routes of the same workload (reported beside the headline, N=1 only) ------------------
+    routes = None
+    if args.gpus == 1 and not args.no_general and args.geometry == "cartesian":
+        routes = {}
+
+        def time_route(name, **kw):
+            try:
+                a2 = g.SparseMatrixAssembler(pr.U, pr.V, strategy, geometry="hex", device=local_rank, **kw)
+                a2._set_form(form); a2._symbolic(form)
+                c2 = a2.comm.handle
+                for _ in range(3):
+                    L.check(lib.graft_numeric(c2, 3))
+                L.check(lib.graft_sync(c2))
+                ts = []
+                for _ in range(5):
+                    L.check(lib.graft_numeric(c2, 3)); L.check(lib.graft_sync(c2))
+                    ts.append(a2.timers()[0][L.T_NUMERIC])
+                ms = float(np.mean(ts))
+                routes[name] = {"ms_per_step": ms, "nnz_per_s": st1["nnz"] / (ms * 1e-3), "frac_of_hbm_peak": B_num / (ms * 1e-3) / 1e9 / peak,
+                                "route": a2.stats()[0]["path"]}
+                a2.close()
+            except Exception as e:  # pragma: no cover
+                routes[name] = {"error": str(e)[:200]}
+
+        # the same mesh given as hex node coordinates: per-cell Jacobians / coefficients (affine cells, tensor-core route)
+        time_route("hex_nodes_affine")
+        # nodes moved by <= 0.1 h (seed 0): general trilinear cells, cell matrices integrated per cell (FP64) and gathered
+        rng = np.random.default_rng(0)
+
+        def perturb(m, xyz):
+            d = rng.uniform(-0.1, 0.1, xyz.shape) * np.asarray(m.h)[None, :]
+            return xyz + d * _interior_mask(m, m.vertex_multi_index())[:, None]
+
+        time_route("hex_nodes_perturbed", perturb=perturb)
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------
     e2e = None
@@ -295,8 +366,7 @@ def main():
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.ref_cells, 2, 1)
-        cpu = {"value": r["nnz"] / r["seconds"], "unit": "nnz/s", "cores": 1, "kind": "port",
-               "sample": f"{args.ref_cells}^3-cell single-part sample of the same workload, numpy oracle (COO materialisation + COO->CSR), {r['seconds']:.2f} s/step",
+        cpu = {"value": r["nnz"] / r["seconds"], "unit": "nnz/s", "cores": r["threads"], "kind": "port", "sample": cpu_sample_text(r),
                "cells_per_s": r["ncells"] / r["seconds"]}
 
     if rank == 0:
@@ -309,12 +379,18 @@ def main():
                            "l2": "inputs+outputs (>9 GB per step) exceed the 126 MB L2; no explicit flush",
                            "symbolic_ms_device": float(tim[L.T_SYMBOLIC]), "symbolic_s_wall": t_symbolic_wall, "host_setup_s": t_setup,
                            "wall_ms_per_step": wall_ms / args.steps},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "spmv": spmv,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "spmv": spmv, "other_routes": routes,
                 "gpu_launches": int(st1["launches"] - st0["launches"]), "clocks": clocks}
         print(json.dumps(line))
     assem.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _interior_mask(m, ijk):
+    """1 for vertices strictly inside the GLOBAL domain (boundary vertices keep their place so that the domain is unchanged)."""
+    gi = ijk + np.asarray(m.cmin)[None, :]
+    return np.all((gi > 0) & (gi < np.asarray(m.ncells_global)[None, :]), axis=1).astype(np.float64)
 
 
 def A_own_nnz(assem, L, lib, ctx):

@@ -101,11 +101,14 @@ class CartesianLocalModel:
         grids = np.meshgrid(*[np.arange(n) for n in self.ncells_local[::-1]], indexing="ij")
         return np.stack([g.ravel() for g in grids[::-1]], axis=1)
 
-    def vertex_coordinates(self):
+    def vertex_multi_index(self):
+        """(nvertices, D) local multi-index of each local vertex, lexicographic x fastest."""
         nv = self.ncells_local + 1
         grids = np.meshgrid(*[np.arange(n) for n in nv[::-1]], indexing="ij")
-        idx = np.stack([g.ravel() for g in grids[::-1]], axis=1)
-        return self.local_origin() + idx * self.h
+        return np.stack([g.ravel() for g in grids[::-1]], axis=1)
+
+    def vertex_coordinates(self):
+        return self.local_origin() + self.vertex_multi_index() * self.h
 
     def cell_vertex_ids(self):
         """(ncells, 2^D) 1-based local vertex ids, x fastest within the cell."""

@@ -1,0 +1,64 @@
+"""Generate the golden fixtures of tests/golden/ from the CPU oracle (oracle/assembly_oracle.py).
+
+The reference (Julia) cannot be imported or run in this image and its own tests hold no golden matrices
+(SURVEY.md 8c), so these fixtures freeze the ORACLE's outputs on the reference's own test configurations: a
+silent change of the oracle (or of the input producers of the host mirror) is then caught on CPU, and the GPU
+parity tests compare the CUDA path against the same files.
+
+    python tests/golden/make_golden.py        # rewrites tests/golden/*.npz
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from helpers import build_problem, neumann_cellvec_2d, oracle_assemble  # noqa: E402
+
+CASES = {
+    # reference test/PoissonTests.jl:14-45 (config 1): 4x4 cells on (0,4)^2, (2,2) parts, Q2, u=(x+y)^2, Neumann on tags 6, 8
+    "poisson_config1_sub": dict(parts=(2, 2), cells=(4, 4), order=2, tags=[1, 2, 3, 5, 7], strategy="sub", domain=[0, 4, 0, 4], source=-4.0,
+                                neumann=True),
+    "poisson_config1_fully": dict(parts=(2, 2), cells=(4, 4), order=2, tags=[1, 2, 3, 5, 7], strategy="fully", domain=[0, 4, 0, 4], source=-4.0,
+                                  neumann=True),
+    # 3-D Q2 on (2,2,2) parts: the small sibling of config 3
+    "poisson_3d_222_sub": dict(parts=(2, 2, 2), cells=(4, 4, 4), order=2, tags="boundary", strategy="sub", domain=None, source=1.0, neumann=False),
+    # reference test/FESpacesTests.jl:61-70: Q1, l = int 1*v
+    "poisson_q1_21_sub": dict(parts=(2, 1), cells=(5, 3), order=1, tags="boundary", strategy="sub", domain=None, source=1.0, neumann=False),
+}
+
+
+def ufun(case):
+    if case["neumann"]:
+        return lambda x: (x[0] + x[1]) ** 2
+    return lambda x: sum(x[d] * (d + 1) for d in range(len(x)))
+
+
+def build(case):
+    pr = build_problem(case["parts"], case["cells"], case["order"], case["tags"], ufun(case), case["strategy"], domain=case["domain"])
+    extra = neumann_cellvec_2d(pr, lambda x, n: 2 * (x[0] + x[1]) * (n[0] + n[1])) if case["neumann"] else None
+    return pr, extra
+
+
+def run(case):
+    pr, extra = build(case)
+    out, _ = oracle_assemble(pr, ("poisson",), source=case["source"], extra_cellvec=extra)
+    d = {}
+    for k, p in enumerate(out):
+        nown = len(p["rows"]["own_to_local"])
+        d[f"p{k}_rows_l2g"] = p["rows"]["l2g"]; d[f"p{k}_rows_l2o"] = p["rows"]["l2o"]; d[f"p{k}_rows_nown"] = np.int64(nown)
+        d[f"p{k}_cols_l2g"] = p["cols"]["l2g"]; d[f"p{k}_cols_l2o"] = p["cols"]["l2o"]
+        d[f"p{k}_cols_nown"] = np.int64(len(p["cols"]["own_to_local"]))
+        d[f"p{k}_rowptr"], d[f"p{k}_colind"], d[f"p{k}_vals"] = p["csr"]
+        d[f"p{k}_b"] = p["b"]
+    d["nparts"] = np.int64(len(out))
+    return d
+
+
+if __name__ == "__main__":
+    for name, case in CASES.items():
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **run(case))
+        print("wrote", name)
