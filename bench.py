@@ -18,9 +18,7 @@ host->device and the assembled CSR values + right-hand side come back device->ho
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -44,44 +42,48 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled DURING the timed region by a thread calling NVML directly (the timed region is
+    tens of milliseconds: an `nvidia-smi -lms` child would not deliver a single sample in it)."""
 
-    def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, index, period_s=0.002):
+        import threading
+
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.th = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as N
+
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            h = N.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for nm, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    time.sleep(period_s)
+
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
         except Exception:
-            self.p = None
+            self.th = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0])); out["sm_max_mhz"] = float(r[1])
-                for nm, v in zip(names, r[3:7]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
-        return out
+        self._stop.set()
+        if self.th is not None:
+            self.th.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 def algorithmic_bytes(nnz, nrows, nd, ncells, D, nnodes_geom):

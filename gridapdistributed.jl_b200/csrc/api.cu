@@ -104,6 +104,9 @@ int32_t graft_ctx_create(graft_comm* c, int32_t part, int32_t device, graft_ctx*
   CUDA_CHECK(cudaDeviceGetAttribute(&x->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->cstream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&x->vstream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_v0, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_v1, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_a, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_b, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_c, cudaEventDisableTiming));
@@ -120,6 +123,7 @@ int32_t graft_ctx_destroy(graft_ctx* x) {
   cudaSetDevice(x->device);
   cudaStreamSynchronize(x->stream);
   cudaStreamSynchronize(x->cstream);
+  cudaStreamSynchronize(x->vstream);
   if (x->comm) {
     for (auto& p : x->comm->ctxs)
       if (p == x) p = nullptr;
@@ -127,15 +131,16 @@ int32_t graft_ctx_destroy(graft_ctx* x) {
     for (auto p : x->comm->ctxs) all_null = all_null && (p == nullptr);
     if (all_null) x->comm->ctxs.clear();
   }
-  cudaEvent_t evs[] = {x->ev_a, x->ev_b, x->ev_c, x->ev_d};
+  cudaEvent_t evs[] = {x->ev_a, x->ev_b, x->ev_c, x->ev_d, x->ev_v0, x->ev_v1};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   for (int i = 0; i < 8; ++i)
     if (x->tev[i]) cudaEventDestroy(x->tev[i]);
-  cudaStream_t s1 = x->stream, s2 = x->cstream;
+  cudaStream_t s1 = x->stream, s2 = x->cstream, s3 = x->vstream;
   delete x;  // frees device buffers
   cudaStreamDestroy(s1);
   cudaStreamDestroy(s2);
+  cudaStreamDestroy(s3);
   API_END
 }
 

@@ -180,6 +180,22 @@ struct RowClasses {
   DevBuf<double> tfrag;
   DevBuf<double> cls_fs;       // per class entry: constant-source factor (rebuilt by every numeric call)
   int64_t nflagged = 0;
+  // T1 row groups: 8 consecutive rows with the same sequence of (class, lifting flag) share one GROUP template, the
+  // concatenation of their row templates = one contiguous span of the value array
+  int64_t ngroups = 0, ngcls = 0, gtmpl_len = 0;
+  DevBuf<int64_t> gstart;      // ngroups + 1: rowptr[8 b]
+  DevBuf<int32_t> gcls;        // ngroups + 1: group class (the last entry is a dummy)
+  DevBuf<int32_t> gmeta;       // int4 per group class: {template offset lo, hi, span length, lifting mask | rows << 8}
+  DevBuf<int32_t> grep;        // per group class: its first group
+  DevBuf<double> gtmpl, gb;    // group templates / right-hand side of the 8 rows (rebuilt by every numeric call)
+  // lifting plan (affine routes): the cells with Dirichlet dofs of the column field get a lifted cell vector
+  // lc[f][li] = sum_{lj Dirichlet} K[li][lj] g_lj once per numeric call; a row that needs lifting subtracts the entries
+  // of its flagged cells (FESpaces.jl:703-715 applied at cell level, like the reference)
+  int64_t nfc = 0, nfent = 0;
+  DevBuf<int32_t> fcell;       // positions of the flagged cells
+  DevBuf<int64_t> frow_ptr;    // nflagged + 1: entries of the flagged rows (same order as flagrows)
+  DevBuf<int32_t> fent, fk;    // per entry of a flagged row: index into lc (f * nd_i + li) or -1; cell position
+  DevBuf<double> lc;           // nfc x nd_i
 };
 
 struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
@@ -232,8 +248,8 @@ struct CommBase;
 struct graft_ctx {
   graft_comm* comm = nullptr;
   int part = 1, device = 0, num_sms = 148;
-  cudaStream_t stream = nullptr, cstream = nullptr;
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+  cudaStream_t stream = nullptr, cstream = nullptr, vstream = nullptr;  // compute, communication, side stream of the rhs kernels
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_v0 = nullptr, ev_v1 = nullptr;
   cudaEvent_t tev[8] = {nullptr};  // timing events: numeric start / integrate / scatter / exchange, spmv start / end
   bool timers_pending = false, spmv_timer_pending = false;
   Mesh mesh;
@@ -320,6 +336,12 @@ struct GatherArgs {
   const int32_t* eids_i; const double* src_free; const double* src_dir;
   const double* extra;      // [cell][nd_i] or NULL
   const double* cellvecs;   // MAT: lifted cell vectors [cell][nd_i]
+  // T1 row groups
+  int64_t ngroups, ngcls, nnz;
+  const int64_t* gstart; const int32_t* gcls; const int4* gmeta; const int32_t* grep; double* gtmpl; double* gb;
+  // lifting plan
+  int64_t nfc, nflagged;
+  const int32_t* fcell; const int64_t* frow_ptr; const int32_t* fent; const int32_t* fk; const int32_t* flagrows; double* lc;
 };
 
 // ------------------------------------------------------------------------------------------------
