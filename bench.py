@@ -317,7 +317,8 @@ def main():
                     L.check(lib.graft_numeric(c2, 3)); L.check(lib.graft_sync(c2))
                     ts.append(a2.timers()[0][L.T_NUMERIC])
                 ms = float(np.mean(ts))
-                routes[name] = {"ms_per_step": ms, "nnz_per_s": st1["nnz"] / (ms * 1e-3), "frac_of_hbm_peak": B_num / (ms * 1e-3) / 1e9 / peak,
+                tm = a2.timers()[0]
+                routes[name] = {"ms_per_step": ms, "phase_ms": {"integrate": float(tm[L.T_INTEGRATE]), "scatter": float(tm[L.T_SCATTER])}, "nnz_per_s": st1["nnz"] / (ms * 1e-3), "frac_of_hbm_peak": B_num / (ms * 1e-3) / 1e9 / peak,
                                 "route": a2.stats()[0]["path"]}
                 a2.close()
             except Exception as e:  # pragma: no cover
