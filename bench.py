@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--ref-cells", type=int, default=32, help="CPU baseline: owned cells per direction per part (one part per host thread)")
     ap.add_argument("--no-general", action="store_true", help="skip the extra measurement of the general (hex-node) route")
     ap.add_argument("--geometry", default="cartesian", choices=["cartesian", "hex"])
+    ap.add_argument("--perturb", action="store_true", help="hex geometry with nodes moved by <= 0.1 h (general trilinear cells)")
     ap.add_argument("--strategy", default="sub", choices=["sub", "fully"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -196,7 +197,12 @@ def main():
     pr = build_problem(parts, cells, 2, "boundary", u, args.strategy, backend=backend)
     t_setup = time.time() - t0
     strategy = g.FullyAssembledRows() if args.strategy == "fully" else g.SubAssembledRows()
-    assem = g.SparseMatrixAssembler(pr.U, pr.V, strategy, geometry=args.geometry, device=local_rank)
+    kw = {}
+    if args.perturb:
+        args.geometry = "hex"
+        prng = np.random.default_rng(0)
+        kw["perturb"] = lambda m, xyz: xyz + prng.uniform(-0.1, 0.1, xyz.shape) * np.asarray(m.h)[None, :] * _interior_mask(m, m.vertex_multi_index())[:, None]
+    assem = g.SparseMatrixAssembler(pr.U, pr.V, strategy, geometry=args.geometry, device=local_rank, **kw)
     dΩ = g.Measure(pr.trian, 4)
     form = g.Poisson(dΩ, source=1.0)
     lib, comm, ctx = assem.comm.lib, assem.comm.handle, assem.comm.ctxs[0]
