@@ -325,7 +325,7 @@ __device__ __forceinline__ void cell_source_vector(const IntegArgs& a, int64_t k
 }
 
 template <int D, int MT>
-__global__ void __launch_bounds__(32) integrate_small_kernel(IntegArgs a, MmaShape sh, int cells_per_block) {
+__global__ void __launch_bounds__(32, 18) integrate_small_kernel(IntegArgs a, MmaShape sh, int cells_per_block) {
   extern __shared__ double sm[];
   const int nv = 1 << D;
   const int lane = threadIdx.x, g8 = lane >> 2, kk = lane & 3;
