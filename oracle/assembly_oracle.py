@@ -403,6 +403,98 @@ def create_from_nz(strategy, I, J, V, b_fe, touched, test_dofs, trial_dofs):
     return out
 
 
+
+# ------------------------------------------------------------------------------------------------
+# A15  block pipeline (reference MultiField.jl:473-560; Algebra.jl:488-496, 508-528, 543-547, 587-591,
+#      990-1009, 1017-1024, 1036-1046, 1146-1169)
+# ------------------------------------------------------------------------------------------------
+
+
+def integrate_stokes_cells(cell_coords, ref_u, ref_p, order_u, order_p, quad_degree, nu, source_u=None, chunk=2048):
+    """Taylor-Hood Stokes blocks of  a((u,p),(v,q)) = ∫ ν ∇v⊙∇u − (∇⋅v) p − q (∇⋅u) dΩ  (reference
+    test/StokesOpenBoundaryTests.jl:44-49) per cell: Kuu[(al,i),(be,j)], Kup[(al,i),j], Kpu[i,(be,j)] and the
+    velocity source vector.  Velocity dofs are component-major (ldof = node + nnodes*comp, A.5)."""
+    ncells, nv, D = cell_coords.shape
+    phiu, dphiu, w, xi = reference_tables(D, order_u, ref_u, quad_degree)
+    phip, _, _, _ = reference_tables(D, order_p, ref_p, quad_degree)
+    _, dN = geometry_tables(D, xi)
+    nu_s, np_s = phiu.shape[1], phip.shape[1]
+    Kuu = np.zeros((ncells, D * nu_s, D * nu_s))
+    Kup = np.zeros((ncells, D * nu_s, np_s))
+    Kpu = np.zeros((ncells, np_s, D * nu_s))
+    Fu = np.zeros((ncells, D * nu_s))
+    for s in range(0, ncells, chunk):
+        X = cell_coords[s : s + chunk]
+        J = np.einsum("cvd,qva->cqda", X, dN)
+        wd = w[None, :] * np.abs(np.linalg.det(J))
+        g = np.einsum("qia,cqad->cqid", dphiu, np.linalg.inv(J))
+        lap = nu * np.einsum("cq,cqid,cqjd->cij", wd, g, g)
+        gv = np.einsum("cq,cqia,qj->caij", wd, g, phip)  # ∫ d_a phi_i psi_j
+        for a in range(D):
+            Kuu[s : s + chunk, a * nu_s : (a + 1) * nu_s, a * nu_s : (a + 1) * nu_s] = lap
+            Kup[s : s + chunk, a * nu_s : (a + 1) * nu_s, :] = -gv[:, a]
+            Kpu[s : s + chunk, :, a * nu_s : (a + 1) * nu_s] = -np.transpose(gv[:, a], (0, 2, 1))
+            if source_u is not None:
+                Fu[s : s + chunk, a * nu_s : (a + 1) * nu_s] = float(source_u) * np.einsum("cq,qi->ci", wd, phiu)
+    return Kuu, Kup, Kpu, Fu
+
+
+def create_from_nz_blocks(strategy, I, J, V, b_fe, touched, test_dofs, trial_dofs):
+    """Block version of create_from_nz.  I[i][j] / J[i][j] / V[i][j]: per-part triplet lists of block (i,j) or None
+    (block untouched by the form); b_fe[i], touched[i]: per-part FE-space vectors of field i; test_dofs[i] /
+    trial_dofs[j]: per-part index sets.  The row PRange of block-row i is built from the union of I over the blocks
+    (i,:), the column PRange of block-column j from the union of J (and owners) over the blocks (:,j), concatenated
+    in block order (Algebra.jl:1146-1169); the ghost-row migration runs per block with rows[i] (:1036-1046)."""
+    nf = len(test_dofs)
+    P = len(test_dofs[0])
+    act = [[I[i][j] is not None for j in range(nf)] for i in range(nf)]
+    G = lambda dofs, L: [dofs[p]["l2g"][np.asarray(L[p], np.int64) - 1] for p in range(P)]
+    Ig = [[G(test_dofs[i], I[i][j]) if act[i][j] else None for j in range(nf)] for i in range(nf)]  # :600-601
+    Jg = [[G(trial_dofs[j], J[i][j]) if act[i][j] else None for j in range(nf)] for i in range(nf)]
+    Vg = [[[np.array(v, np.float64) for v in V[i][j]] if act[i][j] else None for j in range(nf)] for i in range(nf)]
+    cat = lambda lists, p: np.concatenate([l[p] for l in lists]) if lists else np.zeros(0, np.int64)
+    b, brows = [None] * nf, [None] * nf
+    if strategy == "fully":
+        rows = [[setup_prange_without_ghosts(d) for d in test_dofs[i]] for i in range(nf)]
+        for i in range(nf):
+            if b_fe is not None and b_fe[i] is not None:
+                b[i] = [rhs_callback(b_fe[i][p], test_dofs[i][p], rows[i][p]) for p in range(P)]
+        cols = [[setup_prange_with_ghosts(trial_dofs[j][p], cat([Jg[i][j] for i in range(nf) if act[i][j]], p)) for p in range(P)]
+                for j in range(nf)]
+    else:
+        rows = [[setup_prange_with_ghosts(test_dofs[i][p], cat([Ig[i][j] for j in range(nf) if act[i][j]], p)) for p in range(P)]
+                for i in range(nf)]
+        Jo = [[[trial_dofs[j][p]["l2o"][g2l(trial_dofs[j][p], Jg[i][j][p]) - 1] for p in range(P)] if act[i][j] else None
+               for j in range(nf)] for i in range(nf)]
+        for i in range(nf):
+            for j in range(nf):
+                if act[i][j]:
+                    Ig[i][j], Jg[i][j], Jo[i][j], Vg[i][j] = assemble_coo_with_column_owner(Ig[i][j], Jg[i][j], Vg[i][j], rows[i], Jo[i][j])
+        for i in range(nf):
+            if b_fe is not None and b_fe[i] is not None:
+                brows[i] = [prange_from_touched(test_dofs[i][p], touched[i][p]) for p in range(P)]
+                b[i] = [rhs_callback(b_fe[i][p], test_dofs[i][p], brows[i][p]) for p in range(P)]
+        cols = [[setup_prange_with_ghosts(trial_dofs[j][p], cat([Jg[i][j] for i in range(nf) if act[i][j]], p),
+                                          cat([Jo[i][j] for i in range(nf) if act[i][j]], p)) for p in range(P)] for j in range(nf)]
+        for i in range(nf):
+            if b[i] is not None:
+                b[i] = assemble_pvector(b[i], brows[i])
+    out = [[None] * nf for _ in range(nf)]
+    for i in range(nf):
+        jb = min([j for j in range(nf) if act[i][j]], default=-1)  # the vector of block-row i is reported with its first block
+        for j in range(nf):
+            if not act[i][j]:
+                continue
+            res = []
+            for p in range(P):
+                li = g2l(rows[i][p], Ig[i][j][p])
+                lj = g2l(cols[j][p], Jg[i][j][p])
+                csr = coo_to_csr(li, lj, Vg[i][j][p], len(rows[i][p]["l2g"]), len(cols[j][p]["l2g"]))
+                res.append(dict(rows=rows[i][p], cols=cols[j][p], csr=csr, b=None if (b[i] is None or j != jb) else b[i][p],
+                                brows=None if (brows[i] is None or j != jb) else brows[i][p]))
+            out[i][j] = res
+    return out
+
 # ------------------------------------------------------------------------------------------------
 # A14  mul!  ([ext] PartitionedArrays mul!, SURVEY 3.3) and consistent!
 # ------------------------------------------------------------------------------------------------

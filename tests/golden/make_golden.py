@@ -28,24 +28,31 @@ CASES = {
     "poisson_3d_222_sub": dict(parts=(2, 2, 2), cells=(4, 4, 4), order=2, tags="boundary", strategy="sub", domain=None, source=1.0, neumann=False),
     # reference test/FESpacesTests.jl:61-70: Q1, l = int 1*v
     "poisson_q1_21_sub": dict(parts=(2, 1), cells=(5, 3), order=1, tags="boundary", strategy="sub", domain=None, source=1.0, neumann=False),
+    # vector-valued block (config 4 in small): 2-D linear elasticity, Q2 x 2 components, lambda = 1.3, mu = 0.7
+    "elasticity_2d_21_sub": dict(parts=(2, 1), cells=(3, 2), order=2, tags="boundary", strategy="sub", domain=None, source=0.5, neumann=False,
+                                 form=("elasticity", 1.3, 0.7), ncomp=2),
 }
 
 
 def ufun(case):
+    if case.get("ncomp", 1) > 1:
+        D = len(case["cells"])
+        return lambda x: np.stack([x[0] * (d + 1.0) - 0.5 * x[(d + 1) % D] for d in range(D)])
     if case["neumann"]:
         return lambda x: (x[0] + x[1]) ** 2
     return lambda x: sum(x[d] * (d + 1) for d in range(len(x)))
 
 
 def build(case):
-    pr = build_problem(case["parts"], case["cells"], case["order"], case["tags"], ufun(case), case["strategy"], domain=case["domain"])
+    pr = build_problem(case["parts"], case["cells"], case["order"], case["tags"], ufun(case), case["strategy"], domain=case["domain"],
+                       ncomp=case.get("ncomp", 1))
     extra = neumann_cellvec_2d(pr, lambda x, n: 2 * (x[0] + x[1]) * (n[0] + n[1])) if case["neumann"] else None
     return pr, extra
 
 
 def run(case):
     pr, extra = build(case)
-    out, _ = oracle_assemble(pr, ("poisson",), source=case["source"], extra_cellvec=extra)
+    out, _ = oracle_assemble(pr, case.get("form", ("poisson",)), source=case["source"], extra_cellvec=extra)
     d = {}
     for k, p in enumerate(out):
         nown = len(p["rows"]["own_to_local"])
@@ -60,5 +67,7 @@ def run(case):
 
 if __name__ == "__main__":
     for name, case in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run(case))
         print("wrote", name)

@@ -6,7 +6,7 @@ import pytest
 import scipy.sparse.linalg as spla
 
 from gpu_helpers import assert_matches_oracle, build_problem, graft_assemble, oracle_assemble
-from helpers import g, gather_global, l2_error, neumann_cellvec_2d
+from helpers import g, gather_global, l2_error, neumann_cellvec_2d, orc
 
 pytestmark = pytest.mark.gpu
 
@@ -301,4 +301,88 @@ def test_general_cells_multi_part():
     pr = build_problem((2, 2, 1), (4, 4, 2), 2, "boundary", lambda x: x[0] + x[1] * x[2], "sub")
     assem, A, b, out = _perturbed(pr, "poisson", ("poisson",), 1.0)
     assert_matches_oracle(A, b, out)
+    assem.close()
+
+
+# ---- block assembly (config 5: Taylor-Hood Stokes, BlockMultiFieldStyle) ------------------------------------------------
+def _stokes_problem(parts, cells, strategy):
+    from helpers import Problem
+    D = len(cells)
+    pr = Problem()
+    pr.backend = g.DebugBackend(int(np.prod(parts)))
+    pr.model = g.CartesianDiscreteModel(pr.backend, parts, sum(([0.0, 1.0] for _ in cells), []), cells)
+    pr.V = g.TestFESpace(pr.model, g.ReferenceFE("lagrangian", float, 2, ncomp=D), dirichlet_tags="boundary")
+    pr.Q = g.TestFESpace(pr.model, g.ReferenceFE("lagrangian", float, 1), dirichlet_tags=None)
+    pr.U = g.TrialFESpace(lambda x: np.stack([x[(d + 1) % D] * (1.0 - x[d]) + 0.25 * d for d in range(D)]), pr.V)
+    pr.P = g.TrialFESpace(None, pr.Q)
+    pr.strategy, pr.D = strategy, D
+    pr.trian = g.Triangulation(g.FullyAssembledRows(), pr.model) if strategy == "fully" else g.Triangulation(pr.model)
+    return pr
+
+
+def _stokes_oracle(pr, nu, source, perturb=None):
+    from helpers import cell_coords
+    nf = 2
+    spaces = [pr.U, pr.P]
+    dofs = [[orc.local_indices(i.n_global, i.part, i.l2g, i.l2o) for i in sp.gids.indices] for sp in spaces]
+    P = len(pr.model.models)
+    I = [[[None] * P for _ in range(nf)] for _ in range(nf)]
+    J = [[[None] * P for _ in range(nf)] for _ in range(nf)]
+    V = [[[None] * P for _ in range(nf)] for _ in range(nf)]
+    B = [[None] * P for _ in range(nf)]
+    T = [[None] * P for _ in range(nf)]
+    for k, m in enumerate(pr.model.models):
+        lids = pr.trian.cell_lids[k]
+        X = cell_coords(m, lids)
+        if perturb is not None:
+            X = perturb(m, lids, X)
+        su, sp_ = pr.U.spaces[k], pr.P.spaces[k]
+        Kuu, Kup, Kpu, Fu = orc.integrate_stokes_cells(X, su.ref_nodes, sp_.ref_nodes, 2, 1, 4, nu, source)
+        idu, idp = su.cell_dof_ids[lids - 1], sp_.cell_dof_ids[lids - 1]
+        Fp = np.zeros((len(lids), idp.shape[1]))
+        # lifting with the Dirichlet values of both trial fields (FESpaces.jl:703-715; the pressure has none here)
+        Fu = orc.lift_dirichlet(Kuu, Fu, idu, pr.U.dirichlet_values[k])
+        Fu = orc.lift_dirichlet(Kup, Fu, idp, pr.P.dirichlet_values[k])
+        Fp = orc.lift_dirichlet(Kpu, Fp, idu, pr.U.dirichlet_values[k])
+        masks = [(d[k]["l2o"] != d[k]["part"]) if pr.strategy == "fully" else None for d in dofs]
+        I[0][0][k], J[0][0][k], V[0][0][k], B[0][k], T[0][k] = orc.numeric_loop(idu, idu, Kuu, Fu, su.num_free_dofs, masks[0])
+        I[0][1][k], J[0][1][k], V[0][1][k], _, _ = orc.numeric_loop(idu, idp, Kup, None, su.num_free_dofs, masks[0])
+        I[1][0][k], J[1][0][k], V[1][0][k], B[1][k], T[1][k] = orc.numeric_loop(idp, idu, Kpu, Fp, sp_.num_free_dofs, masks[1])
+    I[1][1] = J[1][1] = V[1][1] = None  # the form does not touch the (p,p) block
+    return orc.create_from_nz_blocks(pr.strategy, I, J, V, B, T, dofs, dofs)
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+@pytest.mark.parametrize("geometry", ["cartesian", "hex"])
+@pytest.mark.parametrize("parts,cells", [((1, 1), (4, 3)), ((2, 2), (4, 4)), ((2, 1, 1), (4, 2, 2)), ((2, 2, 2), (4, 4, 4))])
+def test_stokes_blocks_match_oracle(parts, cells, geometry, strategy):
+    pr = _stokes_problem(parts, cells, strategy)
+    st = g.FullyAssembledRows() if strategy == "fully" else g.SubAssembledRows()
+    assem = g.SparseMatrixAssembler([pr.U, pr.P], [pr.V, pr.Q], st, geometry=geometry)
+    form = g.StokesTH(g.Measure(pr.trian, 4), nu=0.7, source=1.5)
+    A, b = g.assemble_matrix_and_vector(form, assem)
+    out = _stokes_oracle(pr, 0.7, 1.5)
+    for i, j in ((0, 0), (0, 1), (1, 0)):  # the right-hand side of block-row i is reported with its first block
+        assert_matches_oracle(A[i][j], b[i], out[i][j], check_b=(j == 0))
+    assem.close()
+
+
+def test_stokes_general_cells_match_oracle():
+    pr = _stokes_problem((1, 1, 1), (3, 2, 2), "sub")
+    rng = np.random.default_rng(3)
+    shift = {}
+
+    def perturb(m, xyz):
+        ijk = m.vertex_multi_index()
+        inside = np.all((ijk > 0) & (ijk < np.asarray(m.ncells_local)[None, :]), axis=1).astype(np.float64)
+        shift[0] = rng.uniform(-0.1, 0.1, xyz.shape) * m.h[None, :] * inside[:, None]
+        return xyz + shift[0]
+
+    assem = g.SparseMatrixAssembler([pr.U, pr.P], [pr.V, pr.Q], g.SubAssembledRows(), geometry="hex", perturb=perturb)
+    form = g.StokesTH(g.Measure(pr.trian, 4), nu=1.3, source=-0.5)
+    A, b = g.assemble_matrix_and_vector(form, assem)
+    assert assem.stats()[0]["path"] == "unfused"
+    out = _stokes_oracle(pr, 1.3, -0.5, perturb=lambda m, lids, X: X + shift[0][m.cell_vertex_ids()[lids - 1] - 1])
+    for i, j in ((0, 0), (0, 1), (1, 0)):
+        assert_matches_oracle(A[i][j], b[i], out[i][j], check_b=(j == 0))
     assem.close()

@@ -39,3 +39,35 @@ def test_mul_alpha_beta(parts, cells, strategy):
     for k, ids in enumerate(A.row_partition.indices):
         assert np.allclose(y.vector_partition[k][: ids.own_length], yo[k], rtol=1e-12, atol=1e-12 * np.abs(yo[k]).max())
     assem.close()
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+def test_mul_on_stokes_blocks(strategy):
+    """mul! on every block of the Taylor-Hood system (reference BlockPartitionedArrays.jl:330-351 applies mul! block by
+    block; test/BlockSparseMatrixAssemblersTests.jl:17-39 checks block == monolithic through mul!)."""
+    import scipy.sparse as sp
+    from test_gpu_assembly import _stokes_oracle, _stokes_problem
+
+    pr = _stokes_problem((2, 2), (4, 4), strategy)
+    st = g.FullyAssembledRows() if strategy == "fully" else g.SubAssembledRows()
+    assem = g.SparseMatrixAssembler([pr.U, pr.P], [pr.V, pr.Q], st)
+    A, b = g.assemble_matrix_and_vector(g.StokesTH(g.Measure(pr.trian, 4), nu=1.0, source=1.0), assem)
+    out = _stokes_oracle(pr, 1.0, 1.0)
+    rng = np.random.default_rng(5)
+    for i, j in ((0, 0), (0, 1), (1, 0)):
+        m, n = out[i][j][0]["rows"]["n"], out[i][j][0]["cols"]["n"]
+        rows, cols, vals = [], [], []
+        for p in out[i][j]:
+            rowptr, colind, val = p["csr"]
+            nown = len(p["rows"]["own_to_local"])
+            rid = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+            keep = rid < nown
+            rows.append(p["rows"]["l2g"][rid[keep]] - 1); cols.append(p["cols"]["l2g"][colind[keep]] - 1); vals.append(val[keep])
+        Ag = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(m, n))
+        xg = rng.uniform(-1, 1, n)
+        x, y = g.pvector_on_cols(A[i][j], xg), g.pvector_on_rows(A[i][j])
+        g.mul(y, A[i][j], x)
+        for k, ids in enumerate(A[i][j].row_partition.indices):
+            ref = (Ag @ xg)[ids.l2g[: ids.own_length] - 1]
+            assert np.allclose(y.vector_partition[k][: ids.own_length], ref, rtol=1e-12, atol=1e-12 * max(np.abs(ref).max(), 1e-300))
+    assem.close()

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
 
-from helpers import build_problem, gather_global, l2_error, neumann_cellvec_2d, oracle_assemble
+from helpers import build_problem, g, gather_global, l2_error, neumann_cellvec_2d, oracle_assemble
 from oracle import assembly_oracle as orc
 
 
@@ -98,3 +98,45 @@ def test_mul_alpha_beta():
         nown = len(p["rows"]["own_to_local"])
         ref = 2.0 * (A @ xg)[p["rows"]["l2g"][:nown] - 1] - 0.5 * y0[:nown]
         assert np.allclose(y, ref, rtol=1e-13, atol=1e-13)
+
+
+def test_stokes_cell_blocks_kats():
+    """Analytic properties of the Taylor-Hood cell blocks: Kpu = Kup^T, the Laplacian rows sum to zero, and a constant
+    velocity is divergence free (Kpu applied to a constant vector vanishes)."""
+    D = 3
+    model = g.CartesianDiscreteModel(g.DebugBackend(1), (1, 1, 1), [0, 2, 0, 1, 0, 3], (2, 1, 2))
+    V = g.TestFESpace(model, g.ReferenceFE("lagrangian", float, 2, ncomp=D), dirichlet_tags=None)
+    Q = g.TestFESpace(model, g.ReferenceFE("lagrangian", float, 1), dirichlet_tags=None)
+    m = model.models[0]
+    X = m.vertex_coordinates()[m.cell_vertex_ids() - 1]
+    Kuu, Kup, Kpu, Fu = orc.integrate_stokes_cells(X, V.spaces[0].ref_nodes, Q.spaces[0].ref_nodes, 2, 1, 4, 0.5, 2.0)
+    assert np.allclose(Kpu, np.transpose(Kup, (0, 2, 1)), atol=1e-14)
+    assert np.abs(Kuu.sum(axis=2)).max() < 1e-12
+    assert np.abs(Kpu @ np.ones(Kpu.shape[2])).max() < 1e-13
+    # source: sum of the cell vector of one component = f * |cell|
+    nds = Kuu.shape[1] // D
+    assert np.allclose(Fu[:, :nds].sum(axis=1), 2.0 * (1.0 * 1.0 * 1.5))
+
+
+def test_block_pipeline_reduces_to_single_field():
+    """create_from_nz_blocks with one field reproduces create_from_nz bit for bit (both strategies)."""
+    for strategy in ("sub", "fully"):
+        pr = build_problem((2, 2), (4, 4), 2, "boundary", lambda x: x[0] + x[1], strategy)
+        out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+        dofs = [orc.local_indices(i.n_global, i.part, i.l2g, i.l2o) for i in pr.U.gids.indices]
+        I, J, Vv, B, T = [], [], [], [], []
+        from helpers import cell_coords
+        for k, (m, s) in enumerate(zip(pr.model.models, pr.U.spaces)):
+            lids = pr.trian.cell_lids[k]
+            K, F = orc.integrate_cells(("poisson",), cell_coords(m, lids), s.ref_nodes, 2, 1, 4, 1.0)
+            ids = s.cell_dof_ids[lids - 1]
+            F = orc.lift_dirichlet(K, F, ids, pr.U.dirichlet_values[k])
+            mask = (dofs[k]["l2o"] != dofs[k]["part"]) if strategy == "fully" else None
+            i, j, v, b, t = orc.numeric_loop(ids, ids, K, F, s.num_free_dofs, mask)
+            I.append(i); J.append(j); Vv.append(v); B.append(b); T.append(t)
+        blk = orc.create_from_nz_blocks(strategy, [[I]], [[J]], [[Vv]], [B], [T], [dofs], [dofs])[0][0]
+        for a, c in zip(out, blk):
+            for u, w in zip(a["csr"], c["csr"]):
+                assert np.array_equal(u, w)
+            assert np.array_equal(a["rows"]["l2g"], c["rows"]["l2g"]) and np.array_equal(a["cols"]["l2g"], c["cols"]["l2g"])
+            assert np.array_equal(a["b"], c["b"])
