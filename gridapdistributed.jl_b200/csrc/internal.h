@@ -250,6 +250,7 @@ struct graft_ctx {
   int part = 1, device = 0, num_sms = 148;
   cudaStream_t stream = nullptr, cstream = nullptr, vstream = nullptr;  // compute, communication, side stream of the rhs kernels
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_v0 = nullptr, ev_v1 = nullptr;
+  cudaEvent_t uev[4] = {nullptr};  // caller's timing marks (graft_mark / graft_elapsed)
   cudaEvent_t tev[8] = {nullptr};  // timing events: numeric start / integrate / scatter / exchange, spmv start / end
   bool timers_pending = false, spmv_timer_pending = false;
   Mesh mesh;

@@ -51,6 +51,8 @@ SIGNATURES = {
     "graft_timers_get": [c_vp, c_vp],
     "graft_stats_get": [c_vp, c_vp],
     "graft_sync": [c_vp],
+    "graft_mark": [c_vp, c_i32],
+    "graft_elapsed": [c_vp, c_i32, c_i32, c_vp],
     "graft_version": [],
 }
 _RESTYPES = {"graft_last_error": C.c_char_p}
