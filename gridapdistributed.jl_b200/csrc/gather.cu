@@ -849,14 +849,19 @@ __global__ void __launch_bounds__(256) stream_groups_kernel(GatherArgs a) {
     double* __restrict__ out = a.vals;
     int64_t p = ((s0 + 3) & ~(int64_t)3) + lane;
     const int64_t pend = min((s1 + 3) & ~(int64_t)3, a.nnz);
-    for (; p + 96 < s1; p += 128) {
-      const double v0 = __ldg(src + p), v1 = __ldg(src + p + 32), v2 = __ldg(src + p + 64), v3 = __ldg(src + p + 96);
-      if (CS) { __stcs(out + p, v0); __stcs(out + p + 32, v1); __stcs(out + p + 64, v2); __stcs(out + p + 96, v3); }
-      else { out[p] = v0; out[p + 32] = v1; out[p + 64] = v2; out[p + 96] = v3; }
-    }
-    for (; p < pend; p += 32) {
-      const double v = p < s1 ? __ldg(src + p) : __ldg(srcn + p);
-      if (CS) __stcs(out + p, v); else out[p] = v;
+    // 4 independent loads in flight per lane in EVERY iteration (the template reads hit L1 only ~60 % of the time)
+    for (; p < pend; p += 128) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = p + 32 * u;
+        v[u] = q < s1 ? __ldg(src + q) : (q < pend ? __ldg(srcn + q) : 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = p + 32 * u;
+        if (q < pend) { if (CS) __stcs(out + q, v[u]); else out[q] = v[u]; }
+      }
     }
   }
   if (VEC) {  // class-constant right-hand side; the rows that need lifting are written by vector_rows_kernel
@@ -1199,9 +1204,27 @@ __global__ void __launch_bounds__(256) cell_lift_kernel(GatherArgs a) {
   const int k = __ldg(a.fcell + f);
   const int32_t* ids = a.eids_j + (int64_t)k * a.nd_j;
   double s = 0.0;
-  for (int lj = 0; lj < a.nd_j; ++lj) {
-    const int id = __ldg(ids + lj);
-    if (id < 0) s += cell_entry<MODE>(a, a.tab, k, li, lj) * __ldg(a.dirvals_j + (-id - 1));
+  if (MODE == GM_T2 && a.ncomp_i == 1 && a.ncomp_j == 1 && a.nS <= 12) {
+    double c[12];  // coefficients of the cell, loaded once
+#pragma unroll
+    for (int mm = 0; mm < 12; ++mm) c[mm] = mm < a.nS ? __ldg(a.cellC + (int64_t)k * a.nS + mm) : 0.0;
+    const int nst = a.nds_i * a.nds_j;
+    for (int lj = 0; lj < a.nd_j; ++lj) {
+      const int id = __ldg(ids + lj);
+      if (id < 0) {
+        const double* S = a.tab + li * a.nds_j + lj;
+        double v = 0.0;
+#pragma unroll
+        for (int mm = 0; mm < 12; ++mm)
+          if (mm < a.nS) v += c[mm] * __ldg(S + mm * nst);
+        s += v * __ldg(a.dirvals_j + (-id - 1));
+      }
+    }
+  } else {
+    for (int lj = 0; lj < a.nd_j; ++lj) {
+      const int id = __ldg(ids + lj);
+      if (id < 0) s += cell_entry<MODE>(a, a.tab, k, li, lj) * __ldg(a.dirvals_j + (-id - 1));
+    }
   }
   a.lc[i] = s;
 }
