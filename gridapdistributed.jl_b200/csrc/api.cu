@@ -103,10 +103,16 @@ int32_t graft_ctx_create(graft_comm* c, int32_t part, int32_t device, graft_ctx*
   x->device = device;
   CUDA_CHECK(cudaDeviceGetAttribute(&x->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUDA_CHECK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&x->cstream, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&x->vstream, cudaStreamNonBlocking));
+  {  // the communication / side streams get the highest priority: their small kernels (packing, NCCL, rhs rows) must be
+     // dispatched as soon as a slot frees up while a large kernel of the compute stream fills the GPU
+    int lo = 0, hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&x->cstream, cudaStreamNonBlocking, hi));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&x->vstream, cudaStreamNonBlocking, hi));
+  }
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_v0, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_v1, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_g, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_a, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_b, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&x->ev_c, cudaEventDisableTiming));
@@ -132,7 +138,7 @@ int32_t graft_ctx_destroy(graft_ctx* x) {
     for (auto p : x->comm->ctxs) all_null = all_null && (p == nullptr);
     if (all_null) x->comm->ctxs.clear();
   }
-  cudaEvent_t evs[] = {x->ev_a, x->ev_b, x->ev_c, x->ev_d, x->ev_v0, x->ev_v1};
+  cudaEvent_t evs[] = {x->ev_a, x->ev_b, x->ev_c, x->ev_d, x->ev_v0, x->ev_v1, x->ev_g};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   for (int i = 0; i < 8; ++i)

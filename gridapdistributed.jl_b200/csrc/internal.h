@@ -251,6 +251,11 @@ struct graft_ctx {
   cudaStream_t stream = nullptr, cstream = nullptr, vstream = nullptr;  // compute, communication, side stream of the rhs kernels
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_v0 = nullptr, ev_v1 = nullptr;
   cudaEvent_t uev[4] = {nullptr};  // caller's timing marks (graft_mark / graft_elapsed)
+  // ghost rows first: a numeric route that computes the ghost rows before the own rows records ev_g when they are
+  // complete, so that their exchange (packing + NCCL on cstream) overlaps the own rows; ev_v1_used: the rhs kernels of
+  // this call run on vstream and finish with ev_v1
+  cudaEvent_t ev_g = nullptr;
+  bool ev_g_valid = false, ev_v1_used = false;
   cudaEvent_t tev[8] = {nullptr};  // timing events: numeric start / integrate / scatter / exchange, spmv start / end
   bool timers_pending = false, spmv_timer_pending = false;
   Mesh mesh;
@@ -340,6 +345,7 @@ struct GatherArgs {
   // T1 row groups
   int64_t ngroups, ngcls, nnz;
   const int64_t* gstart; const int32_t* gcls; const int4* gmeta; const int32_t* grep; double* gtmpl; double* gb;
+  int64_t g_first, g_count;  // groups of this launch
   // lifting plan
   int64_t nfc, nflagged;
   const int32_t* fcell; const int64_t* frow_ptr; const int32_t* fent; const int32_t* fk; const int32_t* flagrows; double* lc;
