@@ -318,7 +318,12 @@ void numeric_fused_affine(graft_ctx* x, int what) {
       }
     }
   }
-  x->d_tab.upload(pack.data(), (int64_t)pack.size(), s);
+  if (x->h_tab.size() != pack.size() || x->d_tab.n != (int64_t)pack.size() ||
+      memcmp(x->h_tab.data(), pack.data(), pack.size() * sizeof(double)) != 0) {
+    x->d_tab.upload(pack.data(), (int64_t)pack.size(), s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    x->h_tab = pack;
+  }
   for (int bi = 0; bi < x->nfields; ++bi) {
     Space& ri = x->fields[bi];
     bool first_vec = true;

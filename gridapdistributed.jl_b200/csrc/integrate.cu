@@ -671,8 +671,12 @@ static void upload_tables(graft_ctx* x, DevTables& T, RefTables* host_tabs /*nfi
       for (int a = 0; a < D; ++a)
         for (int q = 0; q < t.nq; ++q) pack.push_back(t.dN[((size_t)q * nv + v) * D + a]);
   }
-  x->d_tab.upload(pack.data(), (int64_t)pack.size(), x->stream);
-  CUDA_CHECK(cudaStreamSynchronize(x->stream));
+  if (x->h_tab.size() != pack.size() || x->d_tab.n != (int64_t)pack.size() ||
+      memcmp(x->h_tab.data(), pack.data(), pack.size() * sizeof(double)) != 0) {
+    x->d_tab.upload(pack.data(), (int64_t)pack.size(), x->stream);
+    CUDA_CHECK(cudaStreamSynchronize(x->stream));
+    x->h_tab = pack;
+  }
   T.D = D; T.nq = host_tabs[0].nq; T.nv = 1 << D;
   T.dNT = x->d_tab.p + o_dNT;
   for (int f = 0; f < x->nfields; ++f) {

@@ -272,6 +272,8 @@ struct graft_ctx {
   int last_path = 0;  // 1 = unfused (materialised cell matrices), 2 = fused affine
   // device-side tables of the current form/space (tables.cu / integrate.cu)
   DevBuf<double> d_tab;  // packed reference tables
+  std::vector<double> h_tab;  // host copy of what d_tab holds: an unchanged table set is not uploaded again (the upload
+                              // from pageable memory would synchronise the compute stream in every numeric call)
   // scratch for halo'd vectors in graft_spmv (host-buffer variant)
   DevBuf<double> x_dev, y_dev;
   DevBuf<double> cellJinv, celldet;  // per integrated cell: constant inverse Jacobian and |det J| (affine cells)
