@@ -269,14 +269,14 @@ def main():
     B_num = algorithmic_bytes(st1["nnz"], st1["nrows"], sp.nd, st1["ncells"], 3, nnodes_geom)
     peak, peak_src = measured_peak()
     kern_ms = ms_per_step  # the whole numeric step (all its kernels)
-    dominant = {("fused-affine", "cartesian"): "stream_t1_kernel", ("fused-affine", "hex"): "gemm_rows_kernel"}.get(
-        (st1["path"], args.geometry), "integrate_cells_kernel+gather_rows_kernel")
+    dominant = {("fused-affine", "cartesian"): "stream_groups_kernel", ("fused-affine", "hex"): "gemm_rows_kernel"}.get(
+        (st1["path"], args.geometry), "integrate_small_kernel+gather_direct_kernel")
     achieved = B_num / (kern_ms * 1e-3) / 1e9
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if args.cells == 128 and args.gpus == 1:
-            traffic = tj.get(dominant)
+            traffic = sum(tj[k] for k in dominant.split("+")) if all(k in tj for k in dominant.split("+")) else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
