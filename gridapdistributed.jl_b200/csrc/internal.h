@@ -145,6 +145,10 @@ struct Space {
   DevBuf<int32_t> vrcv_row;  // own row index of every received value
   DevBuf<double> vsnd_buf, vrcv_buf;
   DevBuf<int32_t> vsnd_row;  // ghost row (local index in brows) of every sent value, grouped by owner
+  bool vadd_plan = false;    // merged add plan of the vector (see Block::add_plan)
+  int64_t vadd_nu = 0;
+  DevBuf<int64_t> vadd_uslot, vadd_useg;
+  DevBuf<uint32_t> vadd_order;
   // halo plan (consistent!(x): owner -> ghost) on `cols`
   std::vector<int> hsnd_parts, hrcv_parts;
   std::vector<int64_t> hsnd_ptr, hrcv_ptr;
@@ -223,6 +227,12 @@ struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
   DevBuf<int64_t> snd_idx;   // nnz index of every value sent, grouped by owner
   DevBuf<int64_t> rcv_slot;  // nnz index receiving every value, grouped by source
   DevBuf<double> snd_buf, rcv_buf;
+  // merged add plan (built at the first exchange): received values sorted by destination slot, stable in the source
+  // order, so that ONE kernel adds all neighbours' contributions in the same sequence as source-by-source adds
+  bool add_plan = false;
+  int64_t add_nu = 0;
+  DevBuf<int64_t> add_uslot, add_useg;
+  DevBuf<uint32_t> add_order;
   int64_t ghost_nnz_begin = 0;  // = rowptr[n_own_rows]: ghost rows are the tail of the CSR
 };
 
