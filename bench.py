@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--spmv-steps", type=int, default=20)
+    ap.add_argument("--cg-iters", type=int, default=20)
+    ap.add_argument("--no-cg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -310,6 +312,24 @@ def main():
     except Exception as e:  # pragma: no cover
         spmv = {"error": str(e)}
 
+    # ---- Jacobi-CG on top of mul!: a fixed number of iterations on the assembled system ----------------
+    cg = None
+    try:
+        if not args.no_cg:
+            n_own = assem.rows[0].indices[0].own_length
+            bvec = np.empty(st1["nrows"], dtype=np.float64)
+            L.check(lib.graft_vec_get(ctx, 0, L.ptr(bvec)))
+            bs, xs0 = [np.ascontiguousarray(bvec[:n_own])], [np.zeros(n_own)]
+            it, rr = L.c_i32(), L.c_dbl()
+            L.check(lib.graft_cg(comm, 0, L.ptr_array(bs), L.ptr_array(xs0), 0.0, args.cg_iters, 1, C.byref(it), C.byref(rr)))
+            cg_ms = float(assem.timers()[0][L.T_CG])
+            if dist is not None:
+                t = torch.tensor([cg_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); cg_ms = float(t[0])
+            cg = {"iterations": int(it.value), "ms_per_iteration": cg_ms / max(int(it.value), 1), "relres": float(rr.value),
+                  "note": "Jacobi-preconditioned CG, device resident: 1 mul! + 2 global reductions + 3 vector updates per iteration"}
+    except Exception as e:  # pragma: no cover
+        cg = {"error": str(e)[:200]}
+
     # ---- the other geometry routes of the same workload (reported beside the headline, N=1 only) ------------------
     routes = None
     if args.gpus == 1 and not args.no_general and args.geometry == "cartesian":
@@ -393,7 +413,7 @@ def main():
                            "l2": "inputs+outputs (>9 GB per step) exceed the 126 MB L2; no explicit flush",
                            "symbolic_ms_device": float(tim[L.T_SYMBOLIC]), "symbolic_s_wall": t_symbolic_wall, "host_setup_s": t_setup,
                            "wall_ms_per_step": wall_ms / args.steps},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "spmv": spmv, "other_routes": routes,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "spmv": spmv, "cg": cg, "other_routes": routes,
                 "gpu_launches": int(st1["launches"] - st0["launches"]), "clocks": clocks}
         print(json.dumps(line))
     assem.close()

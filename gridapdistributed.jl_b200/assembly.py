@@ -394,8 +394,50 @@ def assemble_matrix_and_vector_b(A, b, form, assem):
     return A, assem._vectors()
 
 
-def mul(c: PVector, A: PSparseMatrix, b: PVector, alpha=1.0, beta=0.0):
-    """``mul!(c,A,b,α,β)``: c_own <- β c_own + α (A b)_own ; b's ghost values are made consistent."""
+class BlockPVector:
+    """``BlockPVector`` (reference BlockPartitionedArrays.jl:45-60): one ``PVector`` per field."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+
+
+class BlockPMatrix:
+    """``BlockPMatrix`` (reference BlockPartitionedArrays.jl:62-78): a grid of ``PSparseMatrix`` blocks."""
+
+    def __init__(self, blocks):
+        self.blocks = [list(r) for r in blocks]
+
+    @property
+    def blocksize(self):
+        return len(self.blocks), len(self.blocks[0])
+
+
+def _is_empty_block(A: PSparseMatrix):
+    lib = A.assem.comm.lib
+    for ctx in A.assem.comm.ctxs:
+        m, n, nnz = L.c_i64(), L.c_i64(), L.c_i64()
+        L.check(lib.graft_csr_query(ctx, A.bi, A.bj, C.byref(m), C.byref(n), C.byref(nnz)))
+        if nnz.value:
+            return False
+    return True
+
+
+def mul(c, A, b, alpha=1.0, beta=0.0):
+    """``mul!(c,A,b,α,β)``: c_own <- β c_own + α (A b)_own ; b's ghost values are made consistent.
+    Block arguments follow reference BlockPartitionedArrays.jl:336-351: y_i <- β y_i, then y_i += α A_ij x_j for every j."""
+    if isinstance(A, BlockPMatrix):
+        ni, nj = A.blocksize
+        for i in range(ni):
+            first = True
+            for j in range(nj):
+                if _is_empty_block(A.blocks[i][j]):  # a block the form does not couple is an empty matrix
+                    continue
+                mul(c.blocks[i], A.blocks[i][j], b.blocks[j], alpha, beta if first else 1.0)
+                first = False
+            if first:  # no coupled block in this block row
+                for v in c.blocks[i].vector_partition:
+                    v[:] = 0.0 if beta == 0.0 else beta * v
+        return c
     assem = A.assem
     xs = [np.ascontiguousarray(v, dtype=np.float64) for v in b.vector_partition]
     ys = [np.ascontiguousarray(v[: ids.own_length], dtype=np.float64) for v, ids in zip(c.vector_partition, A.row_partition.indices)]
@@ -406,6 +448,25 @@ def mul(c: PVector, A: PSparseMatrix, b: PVector, alpha=1.0, beta=0.0):
         v[: len(y)] = y
         bx[:] = x
     return c
+
+
+def cg(A: PSparseMatrix, b: PVector, x0=None, rtol=1e-12, maxit=1000, jacobi=True):
+    """Jacobi-preconditioned CG for ``A x = b`` on the device (``graft_cg``): what a Krylov package does with
+    ``mul!(y,A,x)``; the reference's tests use ``\\`` (gather + LU, test/FESpacesTests.jl:23).  Returns the solution as a
+    PVector on the rows of ``A`` (own values; ghosts zero) and ``(iterations, relative residual)``."""
+    assem = A.assem
+    bs = [np.ascontiguousarray(v[: ids.own_length], dtype=np.float64) for v, ids in zip(b.vector_partition, A.row_partition.indices)]
+    xs = [np.zeros(ids.own_length) if x0 is None else np.ascontiguousarray(v[: ids.own_length], dtype=np.float64)
+          for v, ids in zip((x0.vector_partition if x0 is not None else bs), A.row_partition.indices)]
+    it, rr = L.c_i32(), L.c_dbl()
+    L.check(assem.comm.lib.graft_cg(assem.comm.handle, A.bi, L.ptr_array(bs), L.ptr_array(xs), float(rtol), int(maxit), int(bool(jacobi)),
+                                    C.byref(it), C.byref(rr)))
+    out = []
+    for x, ids in zip(xs, A.row_partition.indices):
+        v = np.zeros(ids.local_length)
+        v[: ids.own_length] = x
+        out.append(v)
+    return PVector(out, A.row_partition), (it.value, rr.value)
 
 
 def pvector_on_cols(A: PSparseMatrix, global_values):

@@ -404,16 +404,20 @@ __global__ void __launch_bounds__(32, 18) integrate_small_kernel(IntegArgs a, Mm
       }
     }
     __syncwarp();
+    // C through shared memory (aliases the operand buffer), leading dimension 40 (= 8 mod 16): the 128-bit stores of the
+    // accumulator pairs (lane = 4 g + kk -> row g, columns 2 kk, 2 kk + 1) are bank-conflict free; rows / columns
+    // beyond M are not stored (the buffer holds M rows)
     double* Cs = A;
+    const int Mr = sh.M;
 #pragma unroll
     for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
       for (int ni = mi; ni < MT; ++ni) {
-        Cs[(size_t)(mi * 8 + g8) * ldc + ni * 8 + 2 * kk] = acc[mi][ni][0];
-        Cs[(size_t)(mi * 8 + g8) * ldc + ni * 8 + 2 * kk + 1] = acc[mi][ni][1];
+        if (mi * 8 + g8 < Mr)
+          *reinterpret_cast<double2*>(Cs + (size_t)(mi * 8 + g8) * ldc + ni * 8 + 2 * kk) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         if (ni > mi) {  // mirror: the epilogue reads C without a case distinction
-          Cs[(size_t)(ni * 8 + 2 * kk) * ldc + mi * 8 + g8] = acc[mi][ni][0];
-          Cs[(size_t)(ni * 8 + 2 * kk + 1) * ldc + mi * 8 + g8] = acc[mi][ni][1];
+          if (ni * 8 + 2 * kk < Mr) Cs[(size_t)(ni * 8 + 2 * kk) * ldc + mi * 8 + g8] = acc[mi][ni][0];
+          if (ni * 8 + 2 * kk + 1 < Mr) Cs[(size_t)(ni * 8 + 2 * kk + 1) * ldc + mi * 8 + g8] = acc[mi][ni][1];
         }
       }
     __syncwarp();
@@ -770,12 +774,12 @@ void integrate_cells_unfused(graft_ctx* x, int what) {
         sh.ld = ((kchunk + 3) / 4) * 4;
         while (sh.ld % 16 != 4) ++sh.ld;
       }
-      sh.ldc = small ? 32 : sh.nt * 8 + 4;
+      sh.ldc = small ? 40 : sh.nt * 8 + 4;
       bool mma_ok = want_mma && !(a.kind == BK_ELAST && !a.same_basis) && (a.kind != BK_GRAD_VAL || a.ncomp_c == 1) &&
                     (a.kind != BK_VAL_GRAD || a.ncomp_r == 1) && (a.kind != BK_ELAST || (a.ncomp_r == D && a.ncomp_c == D));
       size_t geom = (size_t)nv * D + (size_t)a.nq * (((D * D + 1) & ~1) + 2);
       geom += geom & 1;
-      size_t opnd = small ? std::max((size_t)((kchunk + 3) / 4) * 4 * sh.ld, (size_t)32 * sh.ldc)
+      size_t opnd = small ? std::max((size_t)((kchunk + 3) / 4) * 4 * sh.ld, (size_t)sh.M * sh.ldc + 8)
                           : (size_t)(sh.sym ? sh.mt * 8 : (sh.mt + sh.nt) * 8) * sh.ld + (size_t)sh.mt * 8 * sh.ldc;
       size_t smem_mma = 8 * (geom + opnd);
       if (smem_mma > 200 * 1024) mma_ok = false;

@@ -378,5 +378,7 @@ bool fused_affine_available(graft_ctx* ctx);                                // f
 void numeric_fused_affine(graft_ctx* ctx, int what);                        // fused.cu
 void spmv_phase(graft_comm* c, int bi, int bj, double alpha, double* const* x, double beta, double* const* y, bool on_device);  // spmv.cu
 void exchange_ghost_rows(graft_comm* c, int what);                          // numeric.cu
+void cg_solve(graft_comm* c, int blk, const double* const* b_own, double* const* x_own, double rtol, int maxit, int jacobi, int* iters,
+              double* relres);                                               // cg.cu
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

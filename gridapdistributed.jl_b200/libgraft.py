@@ -51,13 +51,14 @@ SIGNATURES = {
     "graft_timers_get": [c_vp, c_vp],
     "graft_stats_get": [c_vp, c_vp],
     "graft_sync": [c_vp],
+    "graft_cg": [c_vp, c_i32, c_vp, c_vp, c_dbl, c_i32, c_i32, P(c_i32), P(c_dbl)],
     "graft_mark": [c_vp, c_i32],
     "graft_elapsed": [c_vp, c_i32, c_i32, c_vp],
     "graft_version": [],
 }
 _RESTYPES = {"graft_last_error": C.c_char_p}
 
-T_SYMBOLIC, T_INTEGRATE, T_SCATTER, T_EXCHANGE, T_NUMERIC, T_SPMV, T_COUNT = 0, 1, 2, 3, 4, 5, 8
+T_SYMBOLIC, T_INTEGRATE, T_SCATTER, T_EXCHANGE, T_NUMERIC, T_SPMV, T_CG, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
 FORM_POISSON, FORM_MASS, FORM_ELASTICITY, FORM_STOKES = 1, 2, 3, 4
 SOURCE_NONE, SOURCE_CONST, SOURCE_NODAL = 0, 1, 2
 
