@@ -185,4 +185,18 @@ function LinearAlgebra.mul!(c::PVector, M::GraftPSparseMatrix, b::PVector, α::N
 end
 LinearAlgebra.mul!(c::PVector, M::GraftPSparseMatrix, b::PVector) = mul!(c, M, b, 1.0, 0.0)
 
+# x = A \ b of the reference's tests (test/FESpacesTests.jl:23: gather to the main part + LU) as Jacobi-CG over the device mul!
+function graft_solve(M::GraftPSparseMatrix, b::PVector; rtol=1e-12, maxit=1000)
+  x = similar(b); fill!(x, 0.0)
+  it = Ref{Cint}(0); rr = Ref{Float64}(0.0)
+  map(own_values(b), own_values(x)) do bo, xo
+    bp = [pointer(bo)]; xp = [pointer(xo)]
+    GC.@preserve bo xo begin
+      @gcheck ccall((:graft_cg, libgraft), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Float64, Cint, Cint, Ref{Cint}, Ref{Float64}),
+                    M.assem.comm, 0, bp, xp, rtol, maxit, 1, it, rr)
+    end
+  end
+  return x, (iterations = it[], relres = rr[])
+end
+
 end # module
