@@ -50,7 +50,7 @@ def assert_matches_oracle(A, b, out, tol=1e-12, check_b=True):
             bo = b.vector_partition[k]
             ref_rows = p["brows"] if p["brows"] is not None else p["rows"]
             assert_same_prange(b.index_partition.indices[k], ref_rows, f"part {k + 1} rows of b")
-            assert np.allclose(bo, p["b"], rtol=tol, atol=tol * max(np.abs(p["b"]).max(), 1e-300)), f"part {k + 1}: b differs"
+            assert np.allclose(bo, p["b"], rtol=tol, atol=tol * max(np.abs(p["b"]).max(initial=0.0), 1e-300)), f"part {k + 1}: b differs"
 
 
 __all__ = ["build_problem", "oracle_assemble", "graft_assemble", "assert_matches_oracle", "assert_same_prange"]

@@ -390,3 +390,52 @@ def test_stokes_general_cells_match_oracle():
     for i, j in ((0, 0), (0, 1), (1, 0)):
         assert_matches_oracle(A[i][j], b[i], out[i][j], check_b=(j == 0))
     assem.close()
+
+
+# ---- the other public entry points of the path and edge cases ------------------------------------------------------------
+def test_separate_matrix_and_vector_entry_points():
+    """assemble_matrix / assemble_vector / allocate_matrix_and_vector / AffineFEOperator reach the same path
+    (reference FESpaces.jl:763-798; rhs through the operator == assemble_vector to 1e-12, test/issue_142.jl:31-34)."""
+    pr = build_problem((2, 2), (5, 4), 2, [1, 2, 5, 7], lambda x: x[0] ** 2 - x[1], "sub")
+    assem, f, A, b = graft_assemble(pr, "poisson", source=2.0)
+    ref_csr = [tuple(a.copy() for a in c) for c in A.csr_arrays()]
+    ref_b = [v.copy() for v in b.vector_partition]
+    A2 = g.assemble_matrix(f, assem)
+    for c0, c1 in zip(ref_csr, A2.csr_arrays()):
+        assert all(np.array_equal(u, v) for u, v in zip(c0, c1))   # same kernels, same order: bitwise
+    b2 = g.assemble_vector(f, assem)
+    for u, v in zip(ref_b, b2.vector_partition):
+        assert np.allclose(u, v, rtol=1e-12, atol=1e-14)
+    A3, none = g.allocate_matrix_and_vector(f, assem)
+    assert none is None
+    for c0, c1 in zip(ref_csr, A3.csr_arrays()):
+        assert np.array_equal(c0[0], c1[0]) and np.array_equal(c0[1], c1[1])
+    op = g.AffineFEOperator(f, pr.U, pr.V, assem)
+    for c0, c1 in zip(ref_csr, op.get_matrix().csr_arrays()):
+        assert all(np.array_equal(u, v) for u, v in zip(c0, c1))
+    for u, v in zip(ref_b, op.get_vector().vector_partition):
+        assert np.array_equal(u, v)
+    assem.close()
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+@pytest.mark.parametrize("parts,cells,order", [((2, 2), (2, 2), 2), ((2, 2, 2), (2, 2, 2), 2), ((4, 1), (4, 1), 1), ((3,), (3,), 2), ((2, 2), (3, 2), 1)])
+def test_one_cell_per_part(parts, cells, order, strategy):
+    """Smallest partitions the reference's block partition produces: one owned cell per part (every other local cell
+    is a ghost), rows that exist on one part only, parts without free own dofs."""
+    D = len(cells)
+    pr = build_problem(parts, cells, order, [1] if D > 1 else [1], lambda x: 1.0 + x[0], strategy)
+    out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+    assem, f, A, b = graft_assemble(pr, "poisson", source=1.0)
+    assert_matches_oracle(A, b, out)
+    assem.close()
+
+
+def test_index_base_one_multi_part_and_vector_valued_fully():
+    pr = build_problem((2, 2), (4, 3), 2, "boundary", _uvec(2), "fully", ncomp=2)
+    out, _ = oracle_assemble(pr, ("elasticity", 0.9, 1.1), source=1.0)
+    assem, f, A, b = graft_assemble(pr, "elasticity", source=1.0, index_base=1, params=(0.9, 1.1))
+    assert_matches_oracle(A, b, out)
+    for (rowptr, colind, val) in A.csr_arrays():
+        assert rowptr[0] == 1 and (len(colind) == 0 or colind.min() >= 1)
+    assem.close()
