@@ -56,6 +56,61 @@ __global__ void __launch_bounds__(256) kB(Args a) {
     if (CS) __stcs(a.vals + p, v); else a.vals[p] = v;
   }
 }
+
+// B2: one warp per group, 16-byte stores (lane writes 2 consecutive doubles), 4 pairs in flight
+template <bool CS>
+__global__ void __launch_bounds__(256) kB2(Args a) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= a.ngroups) return;
+  const long long s0 = __ldg(a.gstart + b), s1 = __ldg(a.gstart + b + 1);
+  const int c0 = __ldg(a.gcls + b), c1 = __ldg(a.gcls + b + 1);
+  const double* src = a.gtmpl + (__ldg(a.goff + c0) - s0);
+  const double* srcn = a.gtmpl + (__ldg(a.goff + c1) - s1);
+  long long p = ((s0 + 3) & ~3ll) + 2 * lane;
+  const long long pend = min((s1 + 3) & ~3ll, a.nnz & ~1ll);
+  for (; p < pend; p += 256) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long q = p + 64 * u;
+      v[u].x = q < s1 ? __ldg(src + q) : (q < pend ? __ldg(srcn + q) : 0.0);
+      v[u].y = q + 1 < s1 ? __ldg(src + q + 1) : (q + 1 < pend ? __ldg(srcn + q + 1) : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long q = p + 64 * u;
+      if (q < pend) { if (CS) __stcs(reinterpret_cast<double2*>(a.vals + q), v[u]); else *reinterpret_cast<double2*>(a.vals + q) = v[u]; }
+    }
+  }
+}
+// B3: like the library kernel now (8-byte stores, 4 in flight in every iteration)
+template <bool CS>
+__global__ void __launch_bounds__(256) kB3(Args a) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= a.ngroups) return;
+  const long long s0 = __ldg(a.gstart + b), s1 = __ldg(a.gstart + b + 1);
+  const int c0 = __ldg(a.gcls + b), c1 = __ldg(a.gcls + b + 1);
+  const double* src = a.gtmpl + (__ldg(a.goff + c0) - s0);
+  const double* srcn = a.gtmpl + (__ldg(a.goff + c1) - s1);
+  long long p = ((s0 + 3) & ~3ll) + lane;
+  const long long pend = min((s1 + 3) & ~3ll, a.nnz);
+  for (; p < pend; p += 128) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long q = p + 32 * u;
+      v[u] = q < s1 ? __ldg(src + q) : (q < pend ? __ldg(srcn + q) : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long q = p + 32 * u;
+      if (q < pend) { if (CS) __stcs(a.vals + q, v[u]); else a.vals[q] = v[u]; }
+    }
+  }
+}
+
 // E: interleaved 256-byte pieces (the pattern of a plain fill kernel): piece -> group table
 template <bool CS>
 __global__ void __launch_bounds__(256) kE(Args a) {
@@ -146,6 +201,11 @@ int main() {
   }
   TIME("B warp/group", (kB<false><<<(unsigned)((ngroups + 7) / 8), 256>>>(a)));
   TIME("B warp/group cs", (kB<true><<<(unsigned)((ngroups + 7) / 8), 256>>>(a)));
+  TIME("B2 warp/group 16B cs", (kB2<true><<<(unsigned)((ngroups + 7) / 8), 256>>>(a)));
+  TIME("B2 warp/group 16B", (kB2<false><<<(unsigned)((ngroups + 7) / 8), 256>>>(a)));
+  TIME("B3 warp/group 4-in-flight cs", (kB3<true><<<(unsigned)((ngroups + 7) / 8), 256>>>(a)));
+  TIME("B3 cs, 128-thread CTAs", (kB3<true><<<(unsigned)((ngroups + 3) / 4), 128>>>(a)));
+  TIME("B3 cs, 512-thread CTAs", (kB3<true><<<(unsigned)((ngroups + 15) / 16), 512>>>(a)));
   for (int bps : {8, 64}) {
     char nm[64];
     snprintf(nm, 64, "E pieces g=148x%d", bps); TIME(nm, (kE<false><<<148 * bps, 256>>>(a)));
