@@ -220,6 +220,9 @@ struct Block {  // matrix block (bi,bj): rows of field bi, cols of field bj
   RowClasses rc;
   DevBuf<double> cellC;         // fused tier 2: per-cell coefficients of this block
   DevBuf<double> cellmats;      // ncells x nd_i x nd_j (unfused route / hook 1)
+  int colperm = 1;              // layout of the columns inside a cell-matrix row: 1 = the local dof order lj = be*nds + j
+                                // (ABI, caller-supplied arrays); ncomp_j = node-major j*ncomp + be (what integrate.cu writes
+                                // for vector-valued columns: the order in which the CSR rows read them)
   DevBuf<double> cellvecs;      // ncells x nd_i (only block (bi,bi) carries the vector of field bi)
   // ghost-row value exchange plan (SubAssembledRows; assemble!(A))
   std::vector<int> snd_parts, rcv_parts;
@@ -342,6 +345,7 @@ struct GatherArgs {
   const double* tab;        // T1: Kbar[nd_i][nd_j] ; T2: S[nS][nds_i][nds_j]
   const double* cellC;      // T2: [cell][ncomp_i][ncomp_j][nS]
   const double* cellmats;   // MAT: [cell][nd_i][nd_j]
+  int colperm;              // MAT: column layout inside a cell-matrix row (Block::colperm)
   double* vals;             // NULL: skip the matrix
   // vector part (b == NULL: skip)
   double* b; int b_accumulate;  // 0: b = source + extra - lift ; 1: b -= lift (later block of a block row)

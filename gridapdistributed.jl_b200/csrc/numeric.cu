@@ -288,6 +288,7 @@ void scatter_user_cellmats(graft_comm* c, int bi, int bj, const double* const* m
     const double* dv = nullptr;
     if (mats && mats[k]) {
       B.cellmats.upload(mats[k], nc * ri.nd * cj.nd, s);
+      B.colperm = 1;  // the ABI layout: columns in local dof order
       dm = B.cellmats.p;
     }
     if (vecs && vecs[k]) {
