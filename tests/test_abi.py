@@ -42,3 +42,28 @@ def test_no_cpu_fallback():
     st = L.load().graft_comm_create_local(1, C.byref(comm))
     assert st != 0
     assert b"no CPU fallback" in L.load().graft_last_error()
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: the package (host mirror + CUDA sources), the header and the Julia shim must not
+    import, link or mention it; only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may."""
+    pkg = os.path.join(ROOT, "gridapdistributed.jl_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        if os.sep + "build" in base or os.sep + "lib" in base or "__pycache__" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"\boracle\b", txt):
+                    offenders.append(os.path.join(base, f))
+    for f in (os.path.join(ROOT, "include", "graft.h"), os.path.join(ROOT, "julia", "GraftAssembly.jl")):
+        if re.search(r"\boracle\b", open(f).read()):
+            offenders.append(f)
+    assert not offenders, offenders
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    # bench.py: the oracle only inside the CPU-baseline function
+    uses = [m.start() for m in re.finditer(r"from oracle|import oracle", bench)]
+    fn = bench.index("def cpu_reference_run")
+    fn_end = bench.index("\ndef ", fn + 1)
+    assert uses and all(fn < u < fn_end for u in uses)
