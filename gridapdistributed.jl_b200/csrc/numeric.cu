@@ -241,6 +241,13 @@ void numeric_phase(graft_comm* c, int what) {
     cudaStream_t s = x->stream;
     x->ev_g_valid = false; x->ev_v1_used = false;
     CUDA_CHECK(cudaEventRecord(x->tev[0], s));
+    if (sweep_available(x)) {
+      CUDA_CHECK(cudaEventRecord(x->tev[1], s));
+      numeric_sweep(x, what);
+      x->last_path = 3;
+      CUDA_CHECK(cudaEventRecord(x->tev[2], s));
+      continue;
+    }
     bool fused = fused_affine_available(x);
     if (fused) {
       CUDA_CHECK(cudaEventRecord(x->tev[1], s));
