@@ -170,7 +170,6 @@ struct RowClasses {
   DevBuf<uint32_t> planes;     // 32 words per plane: (t*nd_j + lj) << 16 | (li*nd_j + lj)
   DevBuf<int32_t> cls_li;      // local row dof of every entry of every class
   DevBuf<uint8_t> cls_pos;     // per (class entry, local col dof): offset of the column inside the row, 0xFF = dropped column
-                               // (rows shorter than 255 only: the sweep route scatters cell-matrix rows with it)
   // batches of up to 8 rows of one class, ordered by first row
   DevBuf<int32_t> brec;        // int4 per batch: {class, rows, len, nent}
   DevBuf<uint32_t> brow;       // 8 per batch: row | needs-lifting flag << 31
@@ -260,6 +259,9 @@ struct Mesh {
 struct SweepPlan {
   bool ok = false;
   int n[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
+  DevBuf<int32_t> erow;    // per (integrated cell, local dof): row of the dof (>= 0), its Dirichlet id (< 0), or SW_NOROW
+  DevBuf<int32_t> rowrec;  // int4 per row: {rowptr lo, rowptr hi, len | cells << 8, first slot of the class in inv16}
+  DevBuf<uint16_t> inv16;  // per (class, nnz slot): 8 x uint16 = where the contribution of the row's t-th cell sits in shared memory
 };
 
 struct Form {
