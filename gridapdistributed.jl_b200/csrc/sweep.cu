@@ -36,18 +36,21 @@
 #define SW_NCS (SW_S * SW_S)
 #define SW_NT 512
 #define SW_NW (SW_NT / 32)
-#define SW_SLOT 676                 // doubles per cell of the current layer: K in the layout of stage 3 (648), f[27], one zero
-#define SW_FV 648
-#define SW_ZERO 675                 // always 0.0: where the address table points when a cell has no column in a slot
-#define SW_FSLOT 336                // doubles per cell of the previous layer: the 3 blocks of K with row node i1 = 2 (324), f[9], zero
-#define SW_FFV 324
-#define SW_FZERO 335
+#define SW_RS 37                    // doubles per (pair u1, row node i2) region of K: 36 + 1 (odd: the regions of the lanes of a warp
+                                    // fall into different shared-memory banks)
+#define SW_BS (3 * SW_RS)           // one block u1
+#define SW_SLOT 696                 // doubles per cell of the current layer: K in the layout of stage 3 (18 regions), f[27], one zero
+#define SW_FV (18 * SW_RS)
+#define SW_ZERO 693                 // always 0.0: where the address table points when a cell has no column in a slot
+#define SW_FSLOT 344                // doubles per cell of the previous layer: the 3 blocks of K with row node i1 = 2, f[9], zero
+#define SW_FFV (3 * SW_BS)
+#define SW_FZERO 342
 #define SW_MAXTASK (SW_NCS * 8)
 #define SW_NOROW 0x7fffffff
 #define SW_EROW ((SW_NCS * 27 + 3) & ~3)   // ints per layer, a multiple of 16 bytes
 #define SW_SMEM_DOUBLES (SW_NCS * (SW_SLOT + SW_FSLOT) + 108 + 10)
 // doubles, then: erow of both layers, task records (int4), task rows, task statics, cell flags, cell coordinates, node table, K offsets
-#define SW_SMEM_BYTES (SW_SMEM_DOUBLES * 8 + 2 * SW_EROW * 4 + SW_MAXTASK * 41 + 3 * SW_NCS * 4 + 27 * 4 + 128 + 732 * 2 + 16)
+#define SW_SMEM_BYTES (SW_SMEM_DOUBLES * 8 + 2 * SW_EROW * 4 + SW_MAXTASK * 60 + 3 * SW_NCS * 4 + 27 * 4 + 128 + 732 * 2 + 16)
 
 __constant__ double c_X[108];       // X[t][u][q]
 __constant__ double c_glx[3], c_glw[3];
@@ -147,7 +150,7 @@ __host__ __device__ inline int sw_kaddr(const int8_t (*tix)[3], int li, int lj) 
   int i1 = tix[li][0], i2 = tix[li][1], i3 = tix[li][2], j1 = tix[lj][0], j2 = tix[lj][1], j3 = tix[lj][2];
   if (i1 > j1) { int t; t = i1; i1 = j1; j1 = t; t = i2; i2 = j2; j2 = t; t = i3; i3 = j3; j3 = t; }
   const int u1s = i1 == 0 ? j1 : (i1 == 1 ? 2 + j1 : 5);
-  return (u1s * 3 + i2) * 36 + i3 * 9 + j2 * 3 + j3;
+  return (u1s * 3 + i2) * SW_RS + i3 * 9 + j2 * 3 + j3;
 }
 // per (class, nnz slot): 8 x uint16, entry t = BYTE offset of the contribution of the row's t-th cell relative to the cell's base
 // in shared memory (current layer: sw_kaddr; previous layer: the same inside the three copied blocks).  A cell without a column
@@ -176,8 +179,8 @@ __global__ void sweep_inv16_kernel(SweepInvArgs a) {
     const int li = a.cls_li[ch.w + t];
     int addr = sw_kaddr(a.tix, li, lj);
     if (a.tix[li][0] == 2) {
-      const int blk = addr / 108;   // 2, 4 or 5
-      addr = (blk == 2 ? 0 : (blk == 4 ? 1 : 2)) * 108 + addr % 108;
+      const int blk = addr / SW_BS;   // 2, 4 or 5
+      addr = (blk == 2 ? 0 : (blk == 4 ? 1 : 2)) * SW_BS + addr % SW_BS;
     }
     tab[((int)p << 3) + t] = (uint16_t)(8 * addr);
   }
@@ -495,12 +498,12 @@ __global__ void __launch_bounds__(SW_NT, 1) sweep_q2_kernel(SweepArgs a, int wha
       SW_TICK(3);
       // ---- stage 2: contract q2, merge the pairs by their type in direction 3:  T2^g[u2] += X_{t2}[u2][q2] T1^{ab}[q2] ----
       if (act) {
-        double* dst = myslot + u1s * 108 + q3r;
+        double* dst = myslot + u1s * SW_BS + q3r;
 #define SW_ST2(T, TT, ACC)                                                                  \
   _Pragma("unroll") for (int u = 0; u < 9; ++u)                                             \
     ACC[u] += c_X[((TT) * 9 + u) * 3 + 0] * T[0] + c_X[((TT) * 9 + u) * 3 + 1] * T[1] + c_X[((TT) * 9 + u) * 3 + 2] * T[2];
 #define SW_ST2_STORE(G, ACC) \
-  _Pragma("unroll") for (int u = 0; u < 9; ++u) dst[(u / 3) * 36 + ((G) * 3 + u % 3) * 3] = ACC[u];
+  _Pragma("unroll") for (int u = 0; u < 9; ++u) dst[(u / 3) * SW_RS + ((G) * 3 + u % 3) * 3] = ACC[u];
         {  // g = 0: pairs (0,0) t2 = 0, (0,1) t2 = 1, (1,0) t2 = 2, (1,1) t2 = 3
           double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
           SW_ST2(T00, 0, acc) SW_ST2(T01, 1, acc) SW_ST2(T10, 2, acc) SW_ST2(T11, 3, acc)
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(SW_NT, 1) sweep_q2_kernel(SweepArgs a, int wha
       //      T2^g[(i2,j2)][q3] and overwrites 9 of them with K[(i1,i2,i3),(j1,j2,j3)] (layout: sw_kaddr) -- no other thread
       //      reads or writes this region, so no barrier and no staging of all 36 values in registers ----
       if (act) {
-        double* R = myslot + (u1s * 3 + q3r) * 36;
+        double* R = myslot + (u1s * 3 + q3r) * SW_RS;
 #pragma unroll 1
         for (int j2 = 0; j2 < 3; ++j2) {
           double in[4][3];
@@ -615,10 +618,10 @@ __global__ void __launch_bounds__(SW_NT, 1) sweep_q2_kernel(SweepArgs a, int wha
     SW_TICK(7);
     // ---- the blocks of K with row node i1 = 2 (the x = 1 face) become the previous layer of the next step ----
     if (have_cur && x < xend) {
-      for (int it = tid; it < ncs * 162; it += SW_NT) {   // 3 blocks x 108 doubles per cell, as 16-byte pieces
-        const int cs = it / 162, r = it - cs * 162, blk = r / 54, off = r - blk * 54;
+      for (int it = tid; it < ncs * SW_FFV; it += SW_NT) {   // 3 blocks per cell
+        const int cs = it / SW_FFV, r = it - cs * SW_FFV, blk = r / SW_BS, off = r - blk * SW_BS;
         const int sblk = blk == 0 ? 2 : (blk == 1 ? 4 : 5);
-        reinterpret_cast<double2*>(front + cs * SW_FSLOT)[r] = reinterpret_cast<const double2*>(cur + cs * SW_SLOT + sblk * 108)[off];
+        front[cs * SW_FSLOT + r] = cur[cs * SW_SLOT + sblk * SW_BS + off];
       }
       for (int it = tid; it < ncs * 9; it += SW_NT) {
         const int cs = it / 9, f = it - cs * 9;
