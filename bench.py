@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- the headline measurement: matrix+vector assembly of 3-D Poisson Q2 on a hex mesh.
+"""bench.py -- the headline measurement: matrix+vector assembly of 3-D Poisson Q2 on a hex mesh (BASELINE.json).
 
-A "step" is one pass of the hot path over one batch of synthetic input: one numeric (re)assembly
-(cell integration + Dirichlet lifting + deterministic scatter + ghost-row reduction) of the whole
-mesh.  N=1: BASELINE.json configs[1] (128^3 cells, one part).  N=2/4/8: parts (2,1,1)/(2,2,1)/(2,2,2),
-128^3 OWNED cells per part (weak scaling; N=8 is configs[2], 256^3 cells), one part per GPU, NCCL
-ghost-row reduction.
+A "step" is one pass of the hot path over one batch of synthetic input: one numeric (re)assembly (cell integration +
+Dirichlet lifting + deterministic scatter + ghost-row reduction) of the whole mesh.  N=1: BASELINE.json configs[1] (128^3
+cells, one part).  N=2/4/8: parts (2,1,1)/(2,2,1)/(2,2,2), 128^3 OWNED cells per part (weak scaling; N=8 is configs[2],
+256^3 cells), one part per GPU, NCCL ghost-row reduction.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells C] [--geometry cartesian|hex]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--form poisson|elasticity|stokes]
+                  [--cells C] [--geometry cartesian|hex|perturbed]
 
-Prints ONE JSON line (rank 0).  `value` = assembled nnz/s with inputs resident in HBM; `e2e` = the same
-through the C ABI with HOST buffers (pinned): per step the Dirichlet values and the source term go
-host->device and the assembled CSR values + right-hand side come back device->host.
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/) on the host cores
-(the Julia reference cannot run in this image: no julia, no MPI).
+Prints ONE JSON line (rank 0).
+  value          assembled nnz/s of the headline geometry, inputs resident in HBM.  For --geometry cartesian (default) this is
+                 the BEST-CASE SPECIAL CASE: the mesh is a Cartesian descriptor, every cell matrix is the same and the numeric
+                 step streams row templates (what Gridap itself exploits for a CartesianDiscreteModel).
+  general_route  the SAME workload with the mesh given as node coordinates moved by <= 0.1 h (general trilinear hexes): per-cell
+                 sum-factorised integration fused with the row reduction (sweep.cu) -- the north-star's kernels (1)+(3); its own
+                 roofline entry.  (N=1, --form poisson.)
+  e2e            the same metric through the C ABI with HOST buffers (pinned): per step the Dirichlet values and the source
+                 term go host->device and the assembled CSR values + right-hand side come back device->host.
+  invariants     size-independent checks of the assembled full-size system, outside the timed region.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/) on the host cores (the Julia reference cannot
+run in this image: no julia, no MPI).  --form elasticity / stokes: BASELINE.json configs[3] / [4] at their per-GPU sizes.
 """
 import argparse
 import json
@@ -25,10 +32,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
-METRIC = "assembled nnz/s (3D Poisson Q2 hex, FP64 matrix+vector assembly)"
+FORMS = {
+    "poisson": dict(cells=128, metric="assembled nnz/s (3D Poisson Q2 hex, FP64 matrix+vector assembly)",
+                    what="3D Poisson Q2 hex"),
+    "elasticity": dict(cells=96, metric="assembled nnz/s (3D linear elasticity vector Q2 hex, 81x81 cell matrices, FP64 matrix+vector assembly)",
+                       what="3D linear elasticity Q2^3 hex (lambda = mu = 1)"),
+    "stokes": dict(cells=64, metric="assembled nnz/s (3D Stokes Taylor-Hood Q2/Q1 hex, block assembly, FP64 matrix+vector assembly)",
+                   what="3D Stokes Taylor-Hood Q2^3/Q1 hex, 2x2 blocks"),
+}
 
 
 def measured_peak():
@@ -39,6 +52,9 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+FP64_PEAK_TFLOPS = 37.0  # measured on this pool's B200 (profiles/r2_fp64_peak.jsonl: DFMA 36.9, DMMA 37.0 TFLOP/s)
 
 
 class ClockSampler:
@@ -86,11 +102,6 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def algorithmic_bytes(nnz, nrows, nd, ncells, D, nnodes_geom):
-    """values written once, rhs written once, cell_dof_ids read once, coordinates read once."""
-    return 8 * nnz + 8 * nrows + 4 * nd * ncells + 8 * D * nnodes_geom
-
-
 def host_parts(nthreads):
     """Factor the host thread count into a 3-D part grid (x fastest gets the largest factor)."""
     p, dims, d = nthreads, [1, 1, 1], 0
@@ -108,12 +119,14 @@ def cpu_reference_run(cells, steps, warmup, threads=None):
     """The reference algorithm on the host cores: oracle/assembly_ref.c (per-cell quadrature, one COO triplet per
     (cell,i,j), COO->CSR sort + duplicate sum), one OS thread per mesh part like one MPI rank per part in the
     reference's with_mpi mode; `cells`^3 owned cells per part, P = host threads parts, no ghost exchange timed."""
-    from helpers import build_problem
+    import graft_import
+
+    g = graft_import.load()
     from oracle import c_oracle
 
     threads = threads or os.cpu_count() or 1
     parts = host_parts(threads)
-    pr = build_problem(parts, tuple(p * cells for p in parts), 2, "boundary", lambda x: x[0] + x[1] + x[2], "sub")
+    pr = g.build_problem(parts, tuple(p * cells for p in parts), 2, "boundary", lambda x: x[0] + x[1] + x[2], "sub")
     inputs = [c_oracle.part_inputs(pr, k) for k in range(len(pr.model.models))]
     times, nnz = [], 0
     for it in range(warmup + steps):
@@ -139,15 +152,182 @@ def run_reference(args):
         return
     r = cpu_reference_run(args.ref_cells, args.steps, min(args.warmup, 1))
     v = r["nnz"] / r["seconds"]
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": FORMS["poisson"]["metric"], "value": v, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"3D Poisson Q2 hex, {r['parts']} parts x {r['cells']}^3 cells on {r['threads']} host threads "
                                    f"(bounded sample of the 128^3-cells-per-GPU workload; the Julia reference cannot run in this image)",
-                       "cells_per_s": r["ncells"] / r["seconds"]},
+                       "cells_per_s": r["ncells"] / r["seconds"], "same_config": False},
             "cpu_baseline": {"value": v, "unit": "nnz/s", "cores": r["threads"], "kind": "port", "sample": cpu_sample_text(r)},
             "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------------------
+class Workload:
+    """One form + geometry on one assembler: problem inputs, blocks, algorithmic bytes."""
+
+    def __init__(self, g, form, parts, cells, strategy, backend):
+        self.g, self.form_name = g, form
+        u3 = lambda x: x[0] + x[1] + x[2]
+        if form == "poisson":
+            self.pr = g.build_problem(parts, cells, 2, "boundary", u3, strategy, backend=backend)
+            self.trials, self.tests, self.blocks = self.pr.U, self.pr.V, [(0, 0)]
+            self.fields = [self.pr.U]
+        elif form == "elasticity":
+            self.pr = g.build_problem(parts, cells, 2, "boundary", lambda x: np.stack([x[0], x[1], x[2]]), strategy, ncomp=3, backend=backend)
+            self.trials, self.tests, self.blocks = self.pr.U, self.pr.V, [(0, 0)]
+            self.fields = [self.pr.U]
+        else:
+            self.pr = g.build_stokes_problem(parts, cells, strategy, backend=backend)
+            self.trials, self.tests, self.blocks = [self.pr.U, self.pr.P], [self.pr.V, self.pr.Q], [(0, 0), (0, 1), (1, 0)]
+            self.fields = [self.pr.U, self.pr.P]
+        self.strategy = g.FullyAssembledRows() if strategy == "fully" else g.SubAssembledRows()
+
+    def make_form(self):
+        g = self.g
+        dO = g.Measure(self.pr.trian, 4)
+        if self.form_name == "poisson":
+            return g.Poisson(dO, source=1.0)
+        if self.form_name == "elasticity":
+            return g.LinearElasticity(dO, 1.0, 1.0, source=1.0)
+        return g.StokesTH(dO, nu=1.0, source=1.0)
+
+    def assembler(self, geometry, device):
+        g = self.g
+        kw = {}
+        if geometry == "perturbed":
+            kw["perturb"] = g.vertex_perturbation(0.1, seed=0)
+        a = g.SparseMatrixAssembler(self.trials, self.tests, self.strategy, geometry="cartesian" if geometry == "cartesian" else "hex",
+                                    device=device, **kw)
+        form = self.make_form()
+        a._set_form(form)
+        return a, form
+
+
+def block_sizes(assem, L, blocks):
+    import ctypes as C
+
+    lib, ctx = assem.comm.lib, assem.comm.ctxs[0]
+    out = {}
+    for (bi, bj) in blocks:
+        m, n, nnz = L.c_i64(), L.c_i64(), L.c_i64()
+        L.check(lib.graft_csr_query(ctx, bi, bj, C.byref(m), C.byref(n), C.byref(nnz)))
+        out[(bi, bj)] = (m.value, n.value, nnz.value)
+    return out
+
+
+def algorithmic_bytes(wl, assem, L, sizes):
+    """values written once, rhs written once, cell_dof_ids read once, coordinates read once (per part)."""
+    st = assem.stats()[0]
+    m_loc = wl.pr.model.models[0]
+    nnodes_geom = int(np.prod(np.asarray(m_loc.ncells_local) + 1))
+    nnz = sum(s[2] for s in sizes.values())
+    nrows = sum(sizes[(f, f)][0] if (f, f) in sizes else sizes[(f, 0)][0] for f in range(len(wl.fields)))
+    nd = sum(U.spaces[0].nd for U in wl.fields)
+    return 8 * nnz + 8 * nrows + 4 * nd * st["ncells"] + 8 * 3 * nnodes_geom, nnz, nrows
+
+
+def own_nnz(assem, L, bi, bj):
+    """nnz of the owned rows of this part (ghost rows are structural zeros owned elsewhere)."""
+    import ctypes as C
+
+    lib, ctx = assem.comm.lib, assem.comm.ctxs[0]
+    m, n, nnz = L.c_i64(), L.c_i64(), L.c_i64()
+    L.check(lib.graft_csr_query(ctx, bi, bj, C.byref(m), C.byref(n), C.byref(nnz)))
+    rowptr = np.empty(m.value + 1, dtype=np.int64)
+    L.check(lib.graft_csr_get(ctx, bi, bj, L.ptr(rowptr), None, None))
+    return int(rowptr[assem.rows[bi].indices[0].own_length] - assem.index_base)
+
+
+def time_steps(assem, L, steps, warmup, barrier, what=3):
+    """EXACTLY `steps` numeric steps enqueued back to back on the library's compute stream, bracketed by timing marks recorded on
+    that stream (graft_mark / graft_elapsed = CUDA events); barrier + synchronize on both sides.  Returns device ms (this rank)."""
+    import ctypes as C
+
+    lib, comm, ctx = assem.comm.lib, assem.comm.handle, assem.comm.ctxs[0]
+    for _ in range(warmup):
+        L.check(lib.graft_numeric(comm, what))
+    L.check(lib.graft_sync(comm))
+    barrier()
+    L.check(lib.graft_mark(comm, 0))
+    for _ in range(steps):
+        L.check(lib.graft_numeric(comm, what))
+    L.check(lib.graft_mark(comm, 1))
+    el = C.c_double()
+    L.check(lib.graft_elapsed(ctx, 0, 1, C.byref(el)))
+    barrier()
+    return float(el.value)
+
+
+def check_invariants(wl, assem, L, torch, dist, cells_global, geometry):
+    """Size-independent properties of the assembled FULL-SIZE system (outside the timed region; device resident through
+    graft_spmv_device).  Poisson / elasticity, block (0,0):
+      nnz        global nnz of the owned rows == ncomp^2 (8N-9)^3  (Q2, Dirichlet on the whole boundary)
+      symmetry   x.(A y) == y.(A x) for two seeded random vectors
+      row_sums   number of owned rows with sum_j A_ij == 0 (to 1e-9 of the largest row sum) == (2N-5)^3: the rows whose stencil avoids the boundary (Poisson)
+      rhs        sum_i (b - A u_h)_i == (1 - 1/(3N))^3 for u = x+y+z, f = 1 (Poisson, unperturbed coordinates)"""
+    import ctypes as C
+
+    lib, comm, ctx = assem.comm.lib, assem.comm.handle, assem.comm.ctxs[0]
+    out = {}
+    rows, cols = assem.rows[0].indices[0], assem.cols[0].indices[0]
+    n_own, n_cols = rows.own_length, cols.local_length
+    ncomp = wl.fields[0].spaces[0].ncomp
+
+    def allsum(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    def spmv(x):
+        y = torch.zeros(max(n_own, 1), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()   # x / y are produced on torch's stream, the product runs on the library's stream
+        L.check(lib.graft_spmv_device(comm, 0, 0, 1.0, L.ptr_array([x.data_ptr()]), 0.0, L.ptr_array([y.data_ptr()])))
+        L.check(lib.graft_sync(comm))
+        return y[:n_own]
+
+    N = cells_global
+    nnz_own = allsum(float(own_nnz(assem, L, 0, 0)))
+    expect = float(ncomp * ncomp) * float(np.prod([8 * n - 9 for n in N]))
+    out["nnz"] = {"got": nnz_own, "expected": expect, "ok": nnz_own == expect}
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + int(os.environ.get("RANK", "0")))
+    x = torch.zeros(n_cols, dtype=torch.float64, device="cuda"); y = torch.zeros(n_cols, dtype=torch.float64, device="cuda")
+    x[:n_own] = torch.rand(n_own, generator=gen, device="cuda", dtype=torch.float64) - 0.5
+    y[:n_own] = torch.rand(n_own, generator=gen, device="cuda", dtype=torch.float64) - 0.5
+    # NB the column PRange lists own dofs first in the same order as the rows (own_to_global of rows == of cols)
+    Ay, Ax = spmv(y), spmv(x)
+    xAy, yAx = allsum(float(torch.dot(x[:n_own], Ay))), allsum(float(torch.dot(y[:n_own], Ax)))
+    scale = allsum(float(torch.dot(Ax, Ax))) ** 0.5 * allsum(float(torch.dot(y[:n_own], y[:n_own]))) ** 0.5
+    out["symmetry"] = {"rel_diff": abs(xAy - yAx) / max(scale, 1e-300), "ok": abs(xAy - yAx) <= 1e-10 * scale}
+    if wl.form_name == "poisson":
+        ones = torch.ones(n_cols, dtype=torch.float64, device="cuda")
+        rs = spmv(ones)
+        # the rows of this operator have |sum| either ~1e-16 |A_ii| (stencil inside the domain) or O(|A_ii|): a threshold of
+        # 1e-9 max|sum| separates them
+        thr = 1e-9 * float(rs.abs().max()) if n_own else 0.0
+        if dist is not None:
+            t = torch.tensor([thr], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); thr = float(t[0])
+        cnt = allsum(float((rs.abs() <= thr).sum()))
+        expect = float(np.prod([2 * n - 5 for n in N]))
+        out["row_sums"] = {"zero_rows": cnt, "expected": expect, "ok": cnt == expect}
+        if geometry != "perturbed":
+            sp = wl.fields[0].spaces[0]
+            fe = wl.fields[0].gids.indices[0]
+            uh_free = sp.free_dof_coords.sum(axis=1)                       # u = x+y+z at the free dofs (FE-space local order)
+            order = np.argsort(fe.l2g, kind="stable")
+            lid = order[np.searchsorted(fe.l2g[order], cols.l2g)]        # column -> FE-space local dof
+            xu = torch.from_numpy(np.ascontiguousarray(uh_free[lid])).cuda()
+            Au = spmv(xu)
+            bvec = np.empty(assem.brows[0].indices[0].local_length, dtype=np.float64)
+            L.check(lib.graft_vec_get(ctx, 0, L.ptr(bvec)))
+            tot = allsum(float(torch.from_numpy(bvec[:n_own]).cuda().sum() - Au.sum()))
+            expect = float(np.prod([1.0 - 1.0 / (3.0 * n) for n in N]))
+            out["rhs"] = {"sum_b_minus_Au": tot, "expected": expect, "ok": abs(tot - expect) <= 1e-9}
+    out["ok"] = all(v["ok"] for v in out.values() if isinstance(v, dict))
+    return out
 
 
 def main():
@@ -156,14 +336,16 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft")
-    ap.add_argument("--cells", type=int, default=128, help="owned cells per direction per part")
+    ap.add_argument("--form", default="poisson", choices=list(FORMS))
+    ap.add_argument("--cells", type=int, default=0, help="owned cells per direction per part (default: 128 / 96 / 64 by form)")
     ap.add_argument("--ref-cells", type=int, default=32, help="CPU baseline: owned cells per direction per part (one part per host thread)")
-    ap.add_argument("--no-general", action="store_true", help="skip the extra measurement of the general (hex-node) route")
-    ap.add_argument("--geometry", default="cartesian", choices=["cartesian", "hex"])
-    ap.add_argument("--perturb", action="store_true", help="hex geometry with nodes moved by <= 0.1 h (general trilinear cells)")
+    ap.add_argument("--no-general", action="store_true", help="skip the measurement of the general (hex-node) routes")
+    ap.add_argument("--geometry", default="cartesian", choices=["cartesian", "hex", "perturbed"])
+    ap.add_argument("--perturb", action="store_true", help="same as --geometry perturbed")
     ap.add_argument("--strategy", default="sub", choices=["sub", "fully"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-invariants", action="store_true")
     ap.add_argument("--spmv-steps", type=int, default=20)
     ap.add_argument("--cg-iters", type=int, default=20)
     ap.add_argument("--no-cg", action="store_true")
@@ -171,13 +353,18 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.perturb:
+        args.geometry = "perturbed"
+    if not args.cells:
+        args.cells = FORMS[args.form]["cells"]
+
+    import ctypes as C
 
     import torch
     import graft_import
 
     g = graft_import.load()
     L = g.libgraft
-    from helpers import build_problem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -195,20 +382,10 @@ def main():
     parts = PARTS[args.gpus]
     cells = tuple(p * args.cells for p in parts)
     t0 = time.time()
-    u = lambda x: x[0] + x[1] + x[2]
-    pr = build_problem(parts, cells, 2, "boundary", u, args.strategy, backend=backend)
+    wl = Workload(g, args.form, parts, cells, args.strategy, backend)
     t_setup = time.time() - t0
-    strategy = g.FullyAssembledRows() if args.strategy == "fully" else g.SubAssembledRows()
-    kw = {}
-    if args.perturb:
-        args.geometry = "hex"
-        prng = np.random.default_rng(0)
-        kw["perturb"] = lambda m, xyz: xyz + prng.uniform(-0.1, 0.1, xyz.shape) * np.asarray(m.h)[None, :] * _interior_mask(m, m.vertex_multi_index())[:, None]
-    assem = g.SparseMatrixAssembler(pr.U, pr.V, strategy, geometry=args.geometry, device=local_rank, **kw)
-    dΩ = g.Measure(pr.trian, 4)
-    form = g.Poisson(dΩ, source=1.0)
+    assem, form = wl.assembler(args.geometry, local_rank)
     lib, comm, ctx = assem.comm.lib, assem.comm.handle, assem.comm.ctxs[0]
-    assem._set_form(form)
     t0 = time.time()
     assem._symbolic(form)
     t_symbolic_wall = time.time() - t0
@@ -219,80 +396,80 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(n, what=3):
-        for _ in range(n):
-            L.check(lib.graft_numeric(comm, what))
-        L.check(lib.graft_sync(comm))
+    def allmax(vals):
+        if dist is None:
+            return list(vals), [0] * len(vals)
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        m = torch.stack(allt)
+        return [float(v) for v in m.max(dim=0).values], [int(i) for i in m.argmax(dim=0)]
 
     # ---- device-resident numeric assembly ---------------------------------------------------------
-    run_steps(args.warmup)
-    st0 = assem.stats()[0]
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    # EXACTLY K steps enqueued back to back on the library's compute stream, bracketed by timing marks recorded on that
-    # stream (graft_mark / graft_elapsed = CUDA events); barrier + synchronize on both sides; max over ranks below
-    import ctypes as C
-
-    t0 = time.perf_counter()
-    L.check(lib.graft_mark(comm, 0))
-    for _ in range(args.steps):
+    for _ in range(args.warmup):
         L.check(lib.graft_numeric(comm, 3))
-    L.check(lib.graft_mark(comm, 1))
-    el = C.c_double()
-    L.check(lib.graft_elapsed(ctx, 0, 1, C.byref(el)))
-    barrier()
+    L.check(lib.graft_sync(comm))
+    st0 = assem.stats()[0]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.perf_counter()
+    dev_ms = time_steps(assem, L, args.steps, 0, barrier)
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     st1 = assem.stats()[0]
-    dev_ms = float(el.value)
-    tim = assem.timers()[0]   # phases of the last step
-    # max over ranks of the device time
+    tim = assem.timers()[0]   # phases of the last step on this rank
+    sizes = block_sizes(assem, L, wl.blocks)
+    B_num, nnz_loc, nrows_loc = algorithmic_bytes(wl, assem, L, sizes)
+    (dev_ms_max, wall_ms, t_int, t_sc, t_ex, t_sym), (arg_dev, _, a_int, a_sc, a_ex, a_sym) = allmax(
+        [dev_ms, wall * 1e3, tim[L.T_INTEGRATE], tim[L.T_SCATTER], tim[L.T_EXCHANGE], tim[L.T_SYMBOLIC]])
     if dist is not None:
-        t = torch.tensor([dev_ms, wall * 1e3], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(t[0]), float(t[1])
-        cnt = torch.tensor([st1["nnz"], st1["ncells"], 0], device="cuda", dtype=torch.int64)
-        # count only OWNED rows' nnz / owned cells for the aggregate
-        m = A_own_nnz(assem, L, lib, ctx)
-        cnt[0] = m
-        cnt[1] = len(pr.model.cell_gids.indices[0].own_to_local)
+        cnt = torch.tensor([sum(own_nnz(assem, L, bi, bj) for (bi, bj) in wl.blocks), len(wl.pr.model.cell_gids.indices[0].own_to_local)],
+                           device="cuda", dtype=torch.int64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         tot_nnz, tot_cells = int(cnt[0]), int(cnt[1])
     else:
-        wall_ms = wall * 1e3
-        tot_nnz, tot_cells = st1["nnz"], st1["ncells"]
-    ms_per_step = dev_ms / args.steps
+        tot_nnz, tot_cells = nnz_loc, st1["ncells"]
+    ms_per_step = dev_ms_max / args.steps
     value = tot_nnz / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (per part)
-    sp = pr.U.spaces[0]
-    m_loc = pr.model.models[0]
-    nnodes_geom = int(np.prod(m_loc.ncells_local + 1))
-    B_num = algorithmic_bytes(st1["nnz"], st1["nrows"], sp.nd, st1["ncells"], 3, nnodes_geom)
     peak, peak_src = measured_peak()
-    kern_ms = ms_per_step  # the whole numeric step (all its kernels)
-    dominant = {("fused-affine", "cartesian"): "stream_groups_kernel", ("fused-affine", "hex"): "gemm_rows_kernel"}.get(
-        (st1["path"], args.geometry), "integrate_small_kernel+gather_direct_kernel")
-    achieved = B_num / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if args.cells == 128 and args.gpus == 1:
-            traffic = sum(tj[k] for k in dominant.split("+")) if all(k in tj for k in dominant.split("+")) else None
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    route = st1["path"]
+    dominant = {("fused-affine", "cartesian"): "stream_groups_kernel", ("fused-affine", "hex"): "gemm_rows_kernel",
+                ("fused-sweep", "hex"): "sweep_q2_kernel", ("fused-sweep", "perturbed"): "sweep_q2_kernel"}.get(
+        (route, args.geometry), "integrate_small_kernel+gather_direct_kernel" if args.form == "poisson" else "integrate_cells_mma_kernel+gather_direct_kernel")
+    achieved = B_num / (ms_per_step * 1e-3) / 1e9
+
+    def traffic_of(kernels):
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed ncu --set full capture (128^3, 1 GPU)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if args.cells == 128 and args.gpus == 1 and args.form == "poisson":
+                return sum(tj[k] for k in kernels.split("+")) if all(k in tj for k in kernels.split("+")) else None
+        except Exception:
+            pass
+        return None
+
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_of(dominant),
                 "kernel": dominant, "algorithmic_bytes_per_launch": B_num, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes / device time of the whole numeric step (all kernels of the step, CUDA events on the library stream)",
-                "phase_ms": {"integrate": float(tim[L.T_INTEGRATE]), "scatter": float(tim[L.T_SCATTER]), "exchange": float(tim[L.T_EXCHANGE])}}
+                "phase_ms_max_over_ranks": {"integrate": t_int, "scatter": t_sc, "exchange": t_ex},
+                "phase_argmax_rank": {"integrate": a_int, "scatter": a_sc, "exchange": a_ex, "step": arg_dev}}
 
-    # ---- SpMV (mul!) device-resident ---------------------------------------------------------------
+    # ---- invariants of the assembled full-size system (outside the timed region) ---------------------
+    invariants = None
+    if not args.no_invariants and args.form in ("poisson", "elasticity"):
+        try:
+            invariants = check_invariants(wl, assem, L, torch, dist, cells, args.geometry)
+        except Exception as e:  # pragma: no cover
+            invariants = {"ok": False, "error": str(e)[:300]}
+
+    # ---- SpMV (mul!) device-resident, block (0,0) --------------------------------------------------
     spmv = None
     try:
-        n_cols = st1["ncols"]; n_own = assem.rows[0].indices[0].own_length
-        x = torch.ones(n_cols, dtype=torch.float64, device="cuda")
+        m00, n00, nnz00 = sizes[(0, 0)]
+        n_own = assem.rows[0].indices[0].own_length
+        x = torch.ones(n00, dtype=torch.float64, device="cuda")
         y = torch.zeros(max(n_own, 1), dtype=torch.float64, device="cuda")
         xs, ys = L.ptr_array([x.data_ptr()]), L.ptr_array([y.data_ptr()])
+        torch.cuda.synchronize()
         for _ in range(3):
             L.check(lib.graft_spmv_device(comm, 0, 0, 1.0, xs, 0.0, ys))
         L.check(lib.graft_sync(comm)); barrier()
@@ -303,86 +480,86 @@ def main():
         el2 = C.c_double()
         L.check(lib.graft_elapsed(ctx, 2, 3, C.byref(el2)))
         barrier()
-        sp_ms = float(el2.value) / args.spmv_steps
-        if dist is not None:
-            t = torch.tensor([sp_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); sp_ms = float(t[0])
-        B_spmv = 12 * st1["nnz"] + 4 * (st1["nrows"] + 1) + 8 * st1["nrows"] + 8 * st1["ncols"]
+        (sp_ms,), _ = allmax([float(el2.value) / args.spmv_steps])
+        B_spmv = 12 * nnz00 + 4 * (m00 + 1) + 8 * m00 + 8 * n00
         spmv = {"ms": sp_ms, "GBps": B_spmv / (sp_ms * 1e-3) / 1e9, "frac_of_peak": B_spmv / (sp_ms * 1e-3) / 1e9 / peak,
-                "algorithmic_bytes": B_spmv}
+                "algorithmic_bytes": B_spmv, "block": [0, 0]}
     except Exception as e:  # pragma: no cover
-        spmv = {"error": str(e)}
+        spmv = {"error": str(e)[:200]}
 
     # ---- Jacobi-CG on top of mul!: a fixed number of iterations on the assembled system ----------------
     cg = None
     try:
-        if not args.no_cg:
+        if not args.no_cg and args.form != "stokes":
             n_own = assem.rows[0].indices[0].own_length
-            bvec = np.empty(st1["nrows"], dtype=np.float64)
+            bvec = np.empty(assem.brows[0].indices[0].local_length, dtype=np.float64)
             L.check(lib.graft_vec_get(ctx, 0, L.ptr(bvec)))
             bs, xs0 = [np.ascontiguousarray(bvec[:n_own])], [np.zeros(n_own)]
             it, rr = L.c_i32(), L.c_dbl()
             L.check(lib.graft_cg(comm, 0, L.ptr_array(bs), L.ptr_array(xs0), 0.0, args.cg_iters, 1, C.byref(it), C.byref(rr)))
-            cg_ms = float(assem.timers()[0][L.T_CG])
-            if dist is not None:
-                t = torch.tensor([cg_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); cg_ms = float(t[0])
+            (cg_ms,), _ = allmax([float(assem.timers()[0][L.T_CG])])
             cg = {"iterations": int(it.value), "ms_per_iteration": cg_ms / max(int(it.value), 1), "relres": float(rr.value),
                   "note": "Jacobi-preconditioned CG, device resident: 1 mul! + 2 global reductions + 3 vector updates per iteration"}
     except Exception as e:  # pragma: no cover
         cg = {"error": str(e)[:200]}
 
-    # ---- the other geometry routes of the same workload (reported beside the headline, N=1 only) ------------------
-    routes = None
+    # ---- the general geometry routes of the same workload (N=1) --------------------------------------------------------
+    routes, general = None, None
     if args.gpus == 1 and not args.no_general and args.geometry == "cartesian":
         routes = {}
 
-        def time_route(name, **kw):
+        def time_route(name, geometry):
             try:
-                a2 = g.SparseMatrixAssembler(pr.U, pr.V, strategy, geometry="hex", device=local_rank, **kw)
-                a2._set_form(form); a2._symbolic(form)
-                c2 = a2.comm.handle
-                for _ in range(3):
-                    L.check(lib.graft_numeric(c2, 3))
-                L.check(lib.graft_sync(c2))
-                ts = []
-                for _ in range(5):
-                    L.check(lib.graft_numeric(c2, 3)); L.check(lib.graft_sync(c2))
-                    ts.append(a2.timers()[0][L.T_NUMERIC])
-                ms = float(np.mean(ts))
+                a2, f2 = wl.assembler(geometry, local_rank)
+                a2._symbolic(f2)
+                ms = time_steps(a2, L, 10, 3, barrier) / 10
                 tm = a2.timers()[0]
-                routes[name] = {"ms_per_step": ms, "phase_ms": {"integrate": float(tm[L.T_INTEGRATE]), "scatter": float(tm[L.T_SCATTER])}, "nnz_per_s": st1["nnz"] / (ms * 1e-3), "frac_of_hbm_peak": B_num / (ms * 1e-3) / 1e9 / peak,
-                                "route": a2.stats()[0]["path"]}
+                r = {"ms_per_step": ms, "phase_ms": {"integrate": float(tm[L.T_INTEGRATE]), "scatter": float(tm[L.T_SCATTER])},
+                     "nnz_per_s": nnz_loc / (ms * 1e-3), "cells_per_s": st1["ncells"] / (ms * 1e-3), "frac_of_hbm_peak": B_num / (ms * 1e-3) / 1e9 / peak,
+                     "route": a2.stats()[0]["path"], "symbolic_ms_device": float(tm[L.T_SYMBOLIC])}
+                if not args.no_invariants and args.form in ("poisson", "elasticity"):
+                    inv = check_invariants(wl, a2, L, torch, dist, cells, geometry)
+                    r["invariants"] = "ok" if inv["ok"] else inv
+                routes[name] = r
                 a2.close()
             except Exception as e:  # pragma: no cover
                 routes[name] = {"error": str(e)[:200]}
 
-        # the same mesh given as hex node coordinates: per-cell Jacobians / coefficients (affine cells, tensor-core route)
-        time_route("hex_nodes_affine")
-        # nodes moved by <= 0.1 h (seed 0): general trilinear cells, cell matrices integrated per cell (FP64) and gathered
-        rng = np.random.default_rng(0)
-
-        def perturb(m, xyz):
-            d = rng.uniform(-0.1, 0.1, xyz.shape) * np.asarray(m.h)[None, :]
-            return xyz + d * _interior_mask(m, m.vertex_multi_index())[:, None]
-
-        time_route("hex_nodes_perturbed", perturb=perturb)
+        # the same mesh given as hex node coordinates (affine cells), and with nodes moved by <= 0.1 h: general trilinear cells
+        time_route("hex_nodes_affine", "hex")
+        time_route("hex_nodes_perturbed", "perturbed")
+        gp = routes.get("hex_nodes_perturbed", {})
+        if "ms_per_step" in gp and args.form == "poisson":
+            # algorithmic flops of the general-cell integration: 2 nq (D nd) nd = 118 098 per cell (dense B^T D B); the
+            # sum-factorised kernel executes 2 x 11 664 + geometry per cell
+            fl_alg, fl_exec = 118098.0 * st1["ncells"], (2 * 11664.0 + 27 * 150.0) * st1["ncells"]
+            general = {"value": gp["nnz_per_s"], "unit": "nnz/s", "ms_per_step": gp["ms_per_step"], "route": gp["route"],
+                       "kernel": "sweep_q2_kernel" if gp["route"] == "fused-sweep" else "integrate_small_kernel+gather_direct_kernel",
+                       "config": "same workload, mesh as node coordinates moved by <= 0.1 h (general trilinear hexes, per-cell Jacobians at 27 points)",
+                       "roofline": {"bound": "hbm", "achieved": B_num / (gp["ms_per_step"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": gp["frac_of_hbm_peak"], "traffic": traffic_of("sweep_q2_kernel"), "algorithmic_bytes_per_launch": B_num},
+                       "fp64": {"algorithmic_tflops": fl_alg / (gp["ms_per_step"] * 1e-3) / 1e12, "executed_tflops": fl_exec / (gp["ms_per_step"] * 1e-3) / 1e12,
+                                "peak_tflops": FP64_PEAK_TFLOPS, "peak_source": "profiles/r2_fp64_peak.jsonl (DFMA/DMMA microbenchmark on this pool)"},
+                       "invariants": gp.get("invariants")}
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------
     e2e = None
     if not args.no_e2e:
-        nnz, nrows = st1["nnz"], st1["nrows"]
-        dv = torch.from_numpy(np.ascontiguousarray(pr.U.dirichlet_values[0])).pin_memory()
-        src = torch.ones(1, dtype=torch.float64).pin_memory()
-        vals = torch.empty(nnz, dtype=torch.float64).pin_memory()
-        bh = torch.empty(nrows, dtype=torch.float64).pin_memory()
-        vp, bp, dvp, srp = vals.numpy(), bh.numpy(), dv.numpy(), src.numpy()
+        dvs = [torch.from_numpy(np.array(U.dirichlet_values[0], dtype=np.float64, copy=True)).pin_memory() for U in wl.fields]
+        src = [torch.ones(U.spaces[0].ncomp, dtype=torch.float64).pin_memory() for U in wl.fields]
+        vals = {b: torch.empty(sizes[b][2], dtype=torch.float64).pin_memory() for b in wl.blocks}
+        bhs = [torch.empty(assem.brows[f].indices[0].local_length, dtype=torch.float64).pin_memory() for f in range(len(wl.fields))]
 
         def e2e_step():
-            if len(dvp):
-                L.check(lib.graft_space_set_dirichlet_values(ctx, 0, len(dvp), L.ptr(dvp)))
-            L.check(lib.graft_source_set(ctx, 0, L.SOURCE_CONST, L.ptr(srp), None))
+            for f, U in enumerate(wl.fields):
+                if len(dvs[f]):
+                    L.check(lib.graft_space_set_dirichlet_values(ctx, f, len(dvs[f]), L.ptr(dvs[f].numpy())))
+            L.check(lib.graft_source_set(ctx, 0, L.SOURCE_CONST, L.ptr(src[0].numpy()), None))
             L.check(lib.graft_numeric(comm, 3))
-            L.check(lib.graft_csr_get_values(ctx, 0, 0, L.ptr(vp)))
-            L.check(lib.graft_vec_get(ctx, 0, L.ptr(bp)))
+            for (bi, bj) in wl.blocks:
+                L.check(lib.graft_csr_get_values(ctx, bi, bj, L.ptr(vals[(bi, bj)].numpy())))
+            for f in range(len(wl.fields)):
+                L.check(lib.graft_vec_get(ctx, f, L.ptr(bhs[f].numpy())))
 
         e2e_steps = max(2, min(args.steps, 5))
         e2e_step(); barrier()
@@ -390,52 +567,40 @@ def main():
         for _ in range(e2e_steps):
             e2e_step()
         barrier()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t[0])
-        e2e = {"value": tot_nnz * e2e_steps / dt, "unit": "nnz/s", "h2d_bytes_per_step": int(8 * len(dvp) + 8),
-               "d2h_bytes_per_step": int(8 * nnz + 8 * nrows), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-               "checksum": float(vp[: min(nnz, 1 << 20)].sum())}
+        (dt,), _ = allmax([time.perf_counter() - t0])
+        v00 = vals[(0, 0)].numpy()
+        e2e = {"value": tot_nnz * e2e_steps / dt, "unit": "nnz/s", "h2d_bytes_per_step": int(sum(8 * len(d) for d in dvs) + 8 * len(src[0])),
+               "d2h_bytes_per_step": int(8 * nnz_loc + 8 * nrows_loc), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "checksum": float(v00[: min(len(v00), 1 << 20)].sum())}
 
     cpu = None
-    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline and args.form == "poisson":
         r = cpu_reference_run(args.ref_cells, 2, 1)
         cpu = {"value": r["nnz"] / r["seconds"], "unit": "nnz/s", "cores": r["threads"], "kind": "port", "sample": cpu_sample_text(r),
                "cells_per_s": r["ncells"] / r["seconds"]}
+    elif rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        cpu = {"value": None, "unit": "nnz/s", "cores": 0, "kind": "port",
+               "sample": "the C restatement (oracle/assembly_ref.c) covers scalar Poisson Q2 only; run --form poisson for the CPU baseline"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        special = (" [best-case special case: Cartesian descriptor, all cell matrices equal, the step streams row templates; see "
+                   "general_route for per-cell integration]") if args.geometry == "cartesian" else ""
+        line = {"metric": FORMS[args.form]["metric"], "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"3D Poisson Q2 hex, {'x'.join(str(c) for c in cells)} cells, parts {parts}, {args.strategy}-assembled rows, "
-                                       f"geometry={args.geometry}, re-assembly (numeric phase) of matrix+vector",
-                           "cells": tot_cells, "nnz": tot_nnz, "cells_per_s": tot_cells / (ms_per_step * 1e-3), "route": st1["path"],
-                           "l2": "inputs+outputs (>9 GB per step) exceed the 126 MB L2; no explicit flush",
-                           "symbolic_ms_device": float(tim[L.T_SYMBOLIC]), "symbolic_s_wall": t_symbolic_wall, "host_setup_s": t_setup,
-                           "wall_ms_per_step": wall_ms / args.steps},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "spmv": spmv, "cg": cg, "other_routes": routes,
+                "config": {"workload": f"{FORMS[args.form]['what']}, {'x'.join(str(c) for c in cells)} cells, parts {parts}, {args.strategy}-assembled rows, "
+                                       f"geometry={args.geometry}, re-assembly (numeric phase) of matrix+vector{special}",
+                           "cells": tot_cells, "nnz": tot_nnz, "cells_per_s": tot_cells / (ms_per_step * 1e-3), "route": route,
+                           "l2": "inputs+outputs (GBs per step) exceed the 126 MB L2; no explicit flush",
+                           "symbolic_ms_device_max_over_ranks": t_sym, "symbolic_argmax_rank": a_sym, "symbolic_s_wall": t_symbolic_wall,
+                           "host_setup_s": t_setup, "wall_ms_per_step": wall_ms / args.steps},
+                "roofline": roofline, "general_route": general, "invariants": ("ok" if invariants and invariants.get("ok") else invariants),
+                "cpu_baseline": cpu, "e2e": e2e, "spmv": spmv, "cg": cg, "other_routes": routes,
                 "gpu_launches": int(st1["launches"] - st0["launches"]), "clocks": clocks}
         print(json.dumps(line))
     assem.close()
     if dist is not None:
         dist.destroy_process_group()
-
-
-def _interior_mask(m, ijk):
-    """1 for vertices strictly inside the GLOBAL domain (boundary vertices keep their place so that the domain is unchanged)."""
-    gi = ijk + np.asarray(m.cmin)[None, :]
-    return np.all((gi > 0) & (gi < np.asarray(m.ncells_global)[None, :]), axis=1).astype(np.float64)
-
-
-def A_own_nnz(assem, L, lib, ctx):
-    """nnz of the owned rows of this part (ghost rows are structural zeros owned elsewhere)."""
-    import ctypes as C
-
-    m, n, nnz = L.c_i64(), L.c_i64(), L.c_i64()
-    L.check(lib.graft_csr_query(ctx, 0, 0, C.byref(m), C.byref(n), C.byref(nnz)))
-    rowptr = np.empty(m.value + 1, dtype=np.int64)
-    L.check(lib.graft_csr_get(ctx, 0, 0, L.ptr(rowptr), None, None))
-    return int(rowptr[assem.rows[0].indices[0].own_length] - assem.index_base)
 
 
 if __name__ == "__main__":

@@ -13,4 +13,5 @@ from .fespaces import ReferenceFE, lagrangian, FESpace, TestFESpace, TrialFESpac
 from .assembly import (SparseMatrixAssembler, GraftSparseMatrixAssembler, assemble_matrix_and_vector, assemble_matrix,
                        assemble_vector, allocate_matrix_and_vector, assemble_matrix_and_vector_b, AffineFEOperator,
                        PSparseMatrix, PVector, BlockPMatrix, BlockPVector, mul, cg, pvector_on_cols, pvector_on_rows, Poisson, Mass, LinearElasticity, StokesTH)
+from .problems import build_problem, build_stokes_problem, vertex_perturbation, interior_vertex_mask
 from . import libgraft

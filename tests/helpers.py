@@ -8,23 +8,8 @@ from oracle import assembly_oracle as orc
 g = graft_import.load()
 
 
-class Problem:
-    pass
-
-
-def build_problem(parts, cells, order=2, tags="boundary", ufun=None, strategy="sub", domain=None, ncomp=1, backend=None):
-    pr = Problem()
-    D = len(parts)
-    pr.backend = backend or g.DebugBackend(int(np.prod(parts)))
-    pr.domain = domain if domain is not None else sum(([0.0, 1.0] for _ in cells), [])
-    pr.model = g.CartesianDiscreteModel(pr.backend, parts, pr.domain, cells)
-    pr.reffe = g.ReferenceFE("lagrangian", float, order, ncomp=ncomp)
-    pr.V = g.TestFESpace(pr.model, pr.reffe, dirichlet_tags=tags)
-    pr.U = g.TrialFESpace(ufun, pr.V)
-    pr.strategy = strategy
-    pr.trian = g.Triangulation(g.FullyAssembledRows(), pr.model) if strategy == "fully" else g.Triangulation(pr.model)
-    pr.D, pr.order, pr.ncomp = D, order, ncomp
-    return pr
+Problem = g.problems.Problem
+build_problem = g.build_problem   # the input producers live in the package (bench.py uses them without importing the oracle)
 
 
 def cell_coords(model_local, cell_lids):
