@@ -27,14 +27,24 @@ def main():
     from helpers import build_problem, gather_global, oracle_assemble
 
     u = lambda x: x[0] * x[1] + 2.0 * x[2]
-    for parts, cells, strategy in [((world, 1, 1), (4 * world, 4, 3), "sub"), ((1, world, 1), (3, 3 * world, 3), "fully")]:
+    grid = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
+    cases = [(grid, tuple(4 * p for p in grid[:2]) + (3 * grid[2],), "sub", "cartesian"),
+             (grid[::-1], tuple(3 * p for p in grid[::-1]), "fully", "cartesian"),
+             (grid, tuple(4 * p for p in grid), "sub", "perturbed"),        # general hexes: the fused sweep route under NCCL
+             (grid, tuple(3 * p for p in grid), "fully", "perturbed")]
+    pert = g.vertex_perturbation(0.1, seed=5)
+    for parts, cells, strategy, geometry in cases:
         ref = build_problem(parts, cells, 2, "boundary", u, strategy)                       # all parts here (oracle side)
-        out, _ = oracle_assemble(ref, ("poisson",), source=1.0)
+        operturb = (lambda m, lids, X: pert(m, m.vertex_coordinates())[m.cell_vertex_ids()[lids - 1] - 1]) if geometry == "perturbed" else None
+        out, _ = oracle_assemble(ref, ("poisson",), source=1.0, perturb=operturb)
         pr = build_problem(parts, cells, 2, "boundary", u, strategy, backend=g.DistBackend())  # my part only
         st = g.FullyAssembledRows() if strategy == "fully" else g.SubAssembledRows()
-        assem = g.SparseMatrixAssembler(pr.U, pr.V, st, device=local_rank)
+        kw = dict(geometry="hex", perturb=pert) if geometry == "perturbed" else {}
+        assem = g.SparseMatrixAssembler(pr.U, pr.V, st, device=local_rank, **kw)
         form = g.Poisson(g.Measure(pr.trian, 4), source=1.0)
         A, b = g.assemble_matrix_and_vector(form, assem)
+        if geometry == "perturbed":
+            assert assem.stats()[0]["path"] == "fused-sweep"
         for rep in range(2):  # second pass: re-assembly (values only)
             p = out[rank]
             assert_same_prange(A.row_partition.indices[0], p["rows"], "rows")
@@ -57,6 +67,8 @@ def main():
         assert rr <= 1e-13
         assert np.allclose(sol.vector_partition[0][: ids.own_length], xref[ids.l2g[: ids.own_length] - 1], rtol=1e-10, atol=1e-10 * np.abs(xref).max())
         assem.close()
+        if rank == 0:
+            print(f"case parts={parts} cells={cells} {strategy} {geometry}: ok on {world} ranks", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")
