@@ -151,9 +151,19 @@ class PSparseMatrix:
         self.assem, self.bi, self.bj = assem, bi, bj
         self.row_partition, self.col_partition = rows, cols
         self._pattern = None
+        # the values are a VIEW of the assembler's device buffers: a later matrix assembly on the same assembler overwrites
+        # them.  The generation stamp turns a read through a stale handle into an error instead of silently wrong values
+        # (the in-place variant assemble_matrix_and_vector_b re-stamps the matrix it is given).
+        self.generation = assem._matrix_generation
+
+    def _check_fresh(self):
+        if self.generation != self.assem._matrix_generation:
+            raise RuntimeError("this PSparseMatrix was overwritten by a later matrix assembly on the same assembler: copy its values "
+                               "(csr_arrays) before re-assembling, or re-assemble in place with assemble_matrix_and_vector_b")
 
     def csr_arrays(self, values_only=False):
         """Per part (rowptr, colind, nzval) in the assembler's index base."""
+        self._check_fresh()
         lib, out = self.assem.comm.lib, []
         for k, ctx in enumerate(self.assem.comm.ctxs):
             m, n, nnz = L.c_i64(), L.c_i64(), L.c_i64()
@@ -217,6 +227,7 @@ class GraftSparseMatrixAssembler:
         self.geometry = geometry
         self._symbolic_key = None
         self._cells_key = None
+        self._matrix_generation = 0
         self.rows = self.cols = None
         lib = self.comm.lib
         for k, ctx in enumerate(self.comm.ctxs):
@@ -304,6 +315,11 @@ class GraftSparseMatrixAssembler:
         self.brows = [self._prange(2, f) for f in range(nf)]
         self._symbolic_key = key
 
+    def _numeric(self, what):
+        if what & 1:
+            self._matrix_generation += 1
+        L.check(self.comm.lib.graft_numeric(self.comm.handle, what))
+
     def _wrap(self):
         nf = len(self.trials)
         mats = [[PSparseMatrix(self, i, j, self.rows[i], self.cols[j]) for j in range(nf)] for i in range(nf)]
@@ -357,7 +373,7 @@ def assemble_matrix_and_vector(form, assem):
     _check_triangulation(form, assem)
     assem._set_form(form)
     assem._symbolic(form)
-    L.check(assem.comm.lib.graft_numeric(assem.comm.handle, 3))
+    assem._numeric(3)
     return assem._wrap(), assem._vectors()
 
 
@@ -365,7 +381,7 @@ def assemble_matrix(form, assem):
     _check_triangulation(form, assem)
     assem._set_form(form)
     assem._symbolic(form)
-    L.check(assem.comm.lib.graft_numeric(assem.comm.handle, 1))
+    assem._numeric(1)
     return assem._wrap()
 
 
@@ -373,7 +389,7 @@ def assemble_vector(form, assem):
     _check_triangulation(form, assem)
     assem._set_form(form)
     assem._symbolic(form)
-    L.check(assem.comm.lib.graft_numeric(assem.comm.handle, 3))  # the lifting needs the cell matrices
+    assem._numeric(2)  # vector only: the matrix values of this assembler are left alone (the lifting evaluates what it needs)
     return assem._vectors()
 
 
@@ -390,8 +406,19 @@ def assemble_matrix_and_vector_b(A, b, form, assem):
     sparsity, index sets and exchange plans are reused; bitwise repeatable."""
     assem._set_form(form)
     assem._symbolic(form)
-    L.check(assem.comm.lib.graft_numeric(assem.comm.handle, 3))
-    return A, assem._vectors()
+    assem._numeric(3)
+    mats = [A] if isinstance(A, PSparseMatrix) else [m for row in A for m in row]
+    for m in mats:
+        m.generation = assem._matrix_generation        # A is the matrix being re-assembled: its handle stays valid
+    new = assem._vectors()
+    if b is not None:                                  # like the reference's `!` variant the caller's b is updated in place
+        olds = [b] if isinstance(b, PVector) else list(b)
+        news = [new] if isinstance(new, PVector) else list(new)
+        for o, n in zip(olds, news):
+            for vo, vn in zip(o.vector_partition, n.vector_partition):
+                vo[...] = vn
+        return A, b
+    return A, new
 
 
 class BlockPVector:
@@ -439,6 +466,7 @@ def mul(c, A, b, alpha=1.0, beta=0.0):
                     v[:] = 0.0 if beta == 0.0 else beta * v
         return c
     assem = A.assem
+    A._check_fresh()
     xs = [np.ascontiguousarray(v, dtype=np.float64) for v in b.vector_partition]
     ys = [np.ascontiguousarray(v[: ids.own_length], dtype=np.float64) for v, ids in zip(c.vector_partition, A.row_partition.indices)]
     for x, ids in zip(xs, A.col_partition.indices):
@@ -455,6 +483,7 @@ def cg(A: PSparseMatrix, b: PVector, x0=None, rtol=1e-12, maxit=1000, jacobi=Tru
     ``mul!(y,A,x)``; the reference's tests use ``\\`` (gather + LU, test/FESpacesTests.jl:23).  Returns the solution as a
     PVector on the rows of ``A`` (own values; ghosts zero) and ``(iterations, relative residual)``."""
     assem = A.assem
+    A._check_fresh()
     bs = [np.ascontiguousarray(v[: ids.own_length], dtype=np.float64) for v, ids in zip(b.vector_partition, A.row_partition.indices)]
     xs = [np.zeros(ids.own_length) if x0 is None else np.ascontiguousarray(v[: ids.own_length], dtype=np.float64)
           for v, ids in zip((x0.vector_partition if x0 is not None else bs), A.row_partition.indices)]

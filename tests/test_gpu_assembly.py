@@ -443,3 +443,71 @@ def test_index_base_one_multi_part_and_vector_valued_fully():
     for (rowptr, colind, val) in A.csr_arrays():
         assert rowptr[0] == 1 and (len(colind) == 0 or colind.min() >= 1)
     assem.close()
+
+
+# ---- re-assembly entry points: vector-only numeric call, in-place `!` variant, stale handles, new coordinates /
+# ---- Dirichlet values -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("geometry", ["cartesian", "hex"])
+def test_assemble_vector_leaves_the_matrix_alone(geometry):
+    pr = build_problem((2, 1, 1), (5, 4, 3), 2, "boundary", lambda x: x[0] * x[1] - x[2], "sub")
+    assem, f, A, b = graft_assemble(pr, "poisson", source=2.0, geometry=geometry)
+    v0 = [c[2].copy() for c in A.csr_arrays()]
+    f2 = g.Poisson(f.dΩ, source=-1.0)                     # another right-hand side on the same assembler
+    b2 = g.assemble_vector(f2, assem)                     # graft_numeric(comm, 2): vector only
+    for a0, a1 in zip(v0, [c[2] for c in A.csr_arrays(values_only=True)]):
+        assert np.array_equal(a0, a1)                     # A's values are untouched and its handle is still valid
+    out2, _ = oracle_assemble(pr, ("poisson",), source=-1.0)
+    for k, p in enumerate(out2):
+        assert np.allclose(b2.vector_partition[k], p["b"], rtol=1e-12, atol=1e-12 * np.abs(p["b"]).max())
+    assem.close()
+
+
+def test_in_place_variant_updates_b_and_stale_handles_raise():
+    pr = build_problem((2, 2), (5, 4), 2, "boundary", lambda x: x[0] - x[1], "sub")
+    assem, f, A, b = graft_assemble(pr, "poisson", source=1.0)
+    f2 = g.Poisson(f.dΩ, source=4.0)
+    A_ret, b_ret = g.assemble_matrix_and_vector_b(A, b, f2, assem)   # reference: assemble_matrix_and_vector!(A,b,assem,data)
+    assert A_ret is A and b_ret is b
+    out2, _ = oracle_assemble(pr, ("poisson",), source=4.0)
+    assert_matches_oracle(A, b, out2)                                # the caller's b holds the new values
+    A_new = g.assemble_matrix(g.Mass(f.dΩ), assem)                   # a second form on the same assembler overwrites the values
+    with pytest.raises(RuntimeError):
+        A.csr_arrays()
+    outm, _ = oracle_assemble(pr, ("mass",), source=None)
+    assert_matches_oracle(A_new, None, outm, check_b=False)
+    assem.close()
+
+
+def test_new_coordinates_and_dirichlet_values():
+    """graft_mesh_update_coords (moving mesh: affine -> general -> affine again) and graft_space_set_dirichlet_values
+    (TrialFESpace(u2, V)) followed by a numeric-only re-assembly track the oracle."""
+    L = g.libgraft
+    rng = np.random.default_rng(7)
+    pr = build_problem((1, 1), (6, 5), 2, "boundary", lambda x: x[0] + 2 * x[1], "sub")
+    assem, f, A, b = graft_assemble(pr, "poisson", source=1.0, geometry="hex")
+    out, _ = oracle_assemble(pr, ("poisson",), source=1.0)
+    assert_matches_oracle(A, b, out)
+    assert assem.stats()[0]["path"] == "fused-affine"
+    m = pr.model.models[0]
+    xyz0 = np.ascontiguousarray(m.vertex_coordinates(), dtype=np.float64)
+    ijk = m.vertex_multi_index()
+    inside = np.all((ijk > 0) & (ijk < np.asarray(m.ncells_local)[None, :]), axis=1).astype(np.float64)
+    shift = rng.uniform(-0.1, 0.1, xyz0.shape) * m.h[None, :] * inside[:, None]
+    ctx = assem.comm.ctxs[0]
+    for xyz, path in ((xyz0 + shift, "unfused"), (xyz0, "fused-affine")):
+        xyz = np.ascontiguousarray(xyz)
+        L.check(assem.comm.lib.graft_mesh_update_coords(ctx, len(xyz), L.ptr(xyz)))
+        A, b = g.assemble_matrix_and_vector_b(A, b, f, assem)
+        assert assem.stats()[0]["path"] == path
+        d = xyz - xyz0
+        out, _ = oracle_assemble(pr, ("poisson",), source=1.0, perturb=lambda mm, lids, X: X + d[mm.cell_vertex_ids()[lids - 1] - 1])
+        assert_matches_oracle(A, b, out)
+    # new Dirichlet data u2 on the same space
+    u2 = lambda x: np.sin(x[0]) - x[1] ** 2
+    pr2 = build_problem((1, 1), (6, 5), 2, "boundary", u2, "sub")
+    dv = np.ascontiguousarray(pr2.U.dirichlet_values[0], dtype=np.float64)
+    L.check(assem.comm.lib.graft_space_set_dirichlet_values(ctx, 0, len(dv), L.ptr(dv)))
+    A, b = g.assemble_matrix_and_vector_b(A, b, f, assem)
+    out2, _ = oracle_assemble(pr2, ("poisson",), source=1.0)
+    assert_matches_oracle(A, b, out2)
+    assem.close()
