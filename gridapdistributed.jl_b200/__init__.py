@@ -12,6 +12,6 @@ from .geometry import (CartesianDiscreteModel, Triangulation, Measure, SubAssemb
 from .fespaces import ReferenceFE, lagrangian, FESpace, TestFESpace, TrialFESpace, generate_gids
 from .assembly import (SparseMatrixAssembler, GraftSparseMatrixAssembler, assemble_matrix_and_vector, assemble_matrix,
                        assemble_vector, allocate_matrix_and_vector, assemble_matrix_and_vector_b, AffineFEOperator,
-                       PSparseMatrix, PVector, BlockPMatrix, BlockPVector, mul, cg, pvector_on_cols, pvector_on_rows, Poisson, Mass, LinearElasticity, StokesTH)
+                       PSparseMatrix, PVector, BlockPMatrix, BlockPVector, mul, cg, pvector_on_cols, pvector_on_rows, Poisson, Mass, LinearElasticity, StokesTH, PLaplacian)
 from .problems import build_problem, build_stokes_problem, vertex_perturbation, interior_vertex_mask
 from . import libgraft

@@ -71,6 +71,18 @@ class StokesTH(GraftForm):
         self.params = (float(nu),)
 
 
+class PLaplacian(GraftForm):
+    """State-dependent forms of reference test/PLaplacianTests.jl:24-31 at the state ``uh`` (per part: values on the free dofs):
+    matrix = jacobian j(uh,du,v) = ∫ ∇(v)⋅(dσ∘(∇(du),∇(uh))) dΩ, vector = residual r(uh,v) = ∫ ∇(v)⋅(σ∘∇(uh)) - v*f dΩ with
+    σ(∇u) = (1+∇u⋅∇u)∇u -- what ``residual_and_jacobian!(b,A,op,uh)`` assembles (test/PLaplacianTests.jl:45-52)."""
+
+    form_id = L.FORM_PLAPLACIAN
+
+    def __init__(self, dΩ, uh, source=None):
+        super().__init__(dΩ, source, None)
+        self.uh = uh
+
+
 # ----------------------------------------------------------------------------------------------
 # communicator handling: DebugBackend -> local comm, DistBackend -> NCCL comm
 # ----------------------------------------------------------------------------------------------
@@ -286,6 +298,10 @@ class GraftSparseMatrixAssembler:
                 else:
                     cv = np.ascontiguousarray(np.broadcast_to(np.asarray(src, dtype=np.float64), (s.ncomp,)))
                     L.check(lib.graft_source_set(ctx, f, L.SOURCE_CONST, L.ptr(cv), None))
+                if form.form_id == L.FORM_PLAPLACIAN and f == 0:
+                    uh = np.ascontiguousarray(form.uh[k], dtype=np.float64)
+                    assert len(uh) == s.num_free_dofs
+                    L.check(lib.graft_state_set(ctx, 0, L.ptr(uh) if len(uh) else None))
                 ex = None
                 if form.extra_cellvec is not None:
                     ex = form.extra_cellvec[f][k] if isinstance(form.extra_cellvec, dict) else (form.extra_cellvec[k] if f == 0 else None)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "graft_form_set": [c_vp, c_i32, c_vp, c_i32, c_i32],
     "graft_source_set": [c_vp, c_i32, c_i32, c_vp, c_vp],
     "graft_extra_cellvec_set": [c_vp, c_i32, c_vp],
+    "graft_state_set": [c_vp, c_i32, c_vp],
+    "graft_state_device": [c_vp, c_i32, c_vp],
     "graft_symbolic": [c_vp, c_i32, c_i32],
     "graft_prange_query": [c_vp, c_i32, c_i32, P(c_i64), P(c_i64), P(c_i64)],
     "graft_prange_get": [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
@@ -59,7 +61,7 @@ SIGNATURES = {
 _RESTYPES = {"graft_last_error": C.c_char_p}
 
 T_SYMBOLIC, T_INTEGRATE, T_SCATTER, T_EXCHANGE, T_NUMERIC, T_SPMV, T_CG, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
-FORM_POISSON, FORM_MASS, FORM_ELASTICITY, FORM_STOKES = 1, 2, 3, 4
+FORM_POISSON, FORM_MASS, FORM_ELASTICITY, FORM_STOKES, FORM_PLAPLACIAN = 1, 2, 3, 4, 5
 SOURCE_NONE, SOURCE_CONST, SOURCE_NODAL = 0, 1, 2
 
 

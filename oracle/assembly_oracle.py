@@ -132,6 +132,16 @@ def integrate_cells(form, cell_coords, ref_nodes, order, ncomp, quad_degree, sou
                         blk = blk + mu * lap
                     Kv[:, al, :, be, :] = blk
             K[s : s + chunk] = Kv.reshape(len(X), nd, nd)
+        elif form[0] == "plaplacian":
+            # state-dependent forms of reference test/PLaplacianTests.jl:24-31 at the state uh (nodal cell values form[1]):
+            #   sigma(grad u) = (1 + grad u . grad u) grad u ,  dsigma(grad du, grad u) = 2 (grad u . grad du) grad u + (1 + |grad u|^2) grad du
+            #   jacobian  K[i,j] = int grad phi_i . dsigma(grad phi_j, grad uh) ,  residual  F[i] = int grad phi_i . sigma(grad uh) - phi_i f
+            uc = np.asarray(form[1])[s : s + chunk]                      # (ncells, nds)
+            gu = np.einsum("cqjd,cj->cqd", g, uc)                        # grad uh at the points
+            n2 = np.einsum("cqd,cqd->cq", gu, gu)
+            gi_gu = np.einsum("cqid,cqd->cqi", g, gu)
+            Ks = np.einsum("cq,cqi,cqj->cij", 2.0 * wd, gi_gu, gi_gu) + np.einsum("cq,cqid,cqjd->cij", wd * (1.0 + n2), g, g)
+            F[s : s + chunk] = np.einsum("cq,cqi->ci", wd * (1.0 + n2), gi_gu)
         else:
             raise ValueError(form)
         if form[0] != "elasticity":
@@ -149,7 +159,10 @@ def integrate_cells(form, cell_coords, ref_nodes, order, ncomp, quad_degree, sou
             else:
                 fq = np.full((ncomp, len(X), len(w)), float(source))
             for c in range(ncomp):
-                F[s : s + chunk, c * nds : (c + 1) * nds] = np.einsum("cq,qi,cq->ci", wd, phi, fq[c])
+                if form[0] == "plaplacian":   # residual: ... - int v f
+                    F[s : s + chunk, c * nds : (c + 1) * nds] -= np.einsum("cq,qi,cq->ci", wd, phi, fq[c])
+                else:
+                    F[s : s + chunk, c * nds : (c + 1) * nds] = np.einsum("cq,qi,cq->ci", wd, phi, fq[c])
     return K, F
 
 

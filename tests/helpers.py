@@ -22,8 +22,21 @@ def oracle_dofs(pr):
     return [orc.local_indices(i.n_global, i.part, i.l2g, i.l2o) for i in pr.U.gids.indices]
 
 
-def oracle_assemble(pr, form=("poisson",), source=None, quad_degree=None, extra_cellvec=None, perturb=None):
-    """Run the oracle on every part.  Returns (per-part results, per-part (K,F) cell arrays)."""
+def cell_values(pr, k, free_values):
+    """Values of an FE function on the dofs of the integrated cells of part k (free dofs: free_values, Dirichlet dofs: the
+    Dirichlet values of the trial space)."""
+    s = pr.U.spaces[k]
+    ids = s.cell_dof_ids[pr.trian.cell_lids[k] - 1]
+    dv = np.asarray(pr.U.dirichlet_values[k], dtype=np.float64)
+    d = dv if len(dv) else np.zeros(1)
+    fv = np.asarray(free_values, dtype=np.float64)
+    fv = fv if len(fv) else np.zeros(1)
+    return np.where(ids > 0, fv[np.maximum(ids, 1) - 1], d[np.clip(-ids, 1, len(d)) - 1])
+
+
+def oracle_assemble(pr, form=("poisson",), source=None, quad_degree=None, extra_cellvec=None, perturb=None, state=None):
+    """Run the oracle on every part.  Returns (per-part results, per-part (K,F) cell arrays).
+    form = ("plaplacian",) with state = per-part free values of uh: jacobian and residual at uh (no lifting)."""
     qd = quad_degree or 2 * pr.order
     I, J, V, B, T, KF = [], [], [], [], [], []
     dofs = oracle_dofs(pr)
@@ -33,9 +46,11 @@ def oracle_assemble(pr, form=("poisson",), source=None, quad_degree=None, extra_
         if perturb is not None:
             X = perturb(m, lids, X)
         src = source[1][k] if (isinstance(source, tuple) and source[0] == "nodal") else source
-        K, F = orc.integrate_cells(form, X, s.ref_nodes, pr.order, pr.ncomp, qd, src)
+        fk = ("plaplacian", cell_values(pr, k, state[k])) if form[0] == "plaplacian" else form
+        K, F = orc.integrate_cells(fk, X, s.ref_nodes, pr.order, pr.ncomp, qd, src)
         ids = s.cell_dof_ids[lids - 1]
-        F = orc.lift_dirichlet(K, F, ids, pr.U.dirichlet_values[k])
+        if form[0] != "plaplacian":   # the increment of a nonlinear problem vanishes on the Dirichlet boundary: nothing to lift
+            F = orc.lift_dirichlet(K, F, ids, pr.U.dirichlet_values[k])
         if extra_cellvec is not None:
             F = F + extra_cellvec[k]
         mask = (dofs[k]["l2o"] != dofs[k]["part"]) if pr.strategy == "fully" else None

@@ -1,0 +1,99 @@
+"""State-dependent re-assembly: the jacobian / residual of reference test/PLaplacianTests.jl:24-52 at a
+device-resident state uh -- what residual_and_jacobian!(b,A,op,uh) assembles in a Newton loop -- against the CPU oracle,
+on the general route (any dimension / order) and on the fused sweep route (3-D Q2)."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from gpu_helpers import assert_matches_oracle, build_problem, oracle_assemble
+from helpers import g, gather_global, l2_error
+
+pytestmark = pytest.mark.gpu
+
+
+def _assemble(pr, uh, source, geometry="cartesian", perturb=None, assem=None):
+    strategy = g.FullyAssembledRows() if pr.strategy == "fully" else g.SubAssembledRows()
+    if assem is None:
+        assem = g.SparseMatrixAssembler(pr.U, pr.V, strategy, geometry=geometry, perturb=perturb)
+    form = g.PLaplacian(g.Measure(pr.trian, 2 * pr.order), uh, source=source)
+    A, b = g.assemble_matrix_and_vector(form, assem)
+    return assem, form, A, b
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+@pytest.mark.parametrize("parts,cells,order", [((2, 2), (4, 4), 1), ((2, 2), (5, 4), 2), ((2, 1, 1), (4, 3, 3), 1)])
+def test_jacobian_and_residual_match_oracle(parts, cells, order, strategy):
+    # reference configuration: CartesianDiscreteModel(ranks,(2,2),(0,4,0,4),(4,4)), Q1, both strategies
+    D = len(cells)
+    u = lambda x: sum(x[d] for d in range(D))
+    pr = build_problem(parts, cells, order, "boundary", u, strategy, domain=sum(([0.0, 4.0] for _ in cells), []))
+    rng = np.random.default_rng(11)
+    uh = [rng.uniform(-1, 1, s.num_free_dofs) for s in pr.U.spaces]
+    # the state must be single valued: ghost copies of a dof carry the owner's value
+    glob = np.zeros(pr.U.gids.indices[0].n_global)
+    for ids, v in zip(pr.U.gids.indices, uh):
+        own = ids.l2o == ids.part
+        glob[ids.l2g[own] - 1] = v[own]
+    uh = [glob[ids.l2g - 1] for ids in pr.U.gids.indices]
+    out, _ = oracle_assemble(pr, ("plaplacian",), source=0.7, state=uh)
+    assem, form, A, b = _assemble(pr, uh, 0.7)
+    assert all(s["path"] == "unfused" for s in assem.stats())
+    assert_matches_oracle(A, b, out)
+    assem.close()
+
+
+@pytest.mark.parametrize("parts,cells,strategy", [((1, 1, 1), (5, 4, 4), "sub"), ((2, 2, 1), (6, 6, 4), "sub"), ((1, 2, 1), (4, 6, 3), "fully")])
+def test_sweep_route_with_state_matches_oracle_and_is_repeatable(parts, cells, strategy):
+    u = lambda x: x[0] + x[1] + x[2]
+    pr = build_problem(parts, cells, 2, "boundary", u, strategy)
+    rng = np.random.default_rng(5)
+    glob = rng.uniform(-0.5, 0.5, pr.U.gids.indices[0].n_global)
+    uh = [glob[ids.l2g - 1] for ids in pr.U.gids.indices]
+    pert = g.vertex_perturbation(0.1, seed=2)
+    out, _ = oracle_assemble(pr, ("plaplacian",), source=-1.0, state=uh,
+                             perturb=lambda m, lids, X: pert(m, m.vertex_coordinates())[m.cell_vertex_ids()[lids - 1] - 1])
+    assem, form, A, b = _assemble(pr, uh, -1.0, geometry="hex", perturb=pert)
+    assert all(s["path"] == "fused-sweep" for s in assem.stats())
+    assert_matches_oracle(A, b, out)
+    v0 = [c[2].copy() for c in A.csr_arrays()]
+    b0 = [x.copy() for x in b.vector_partition]
+    # two more "Newton steps": another state, then the first one again -> bitwise the first result
+    uh2 = [0.5 * v for v in uh]
+    A, b = g.assemble_matrix_and_vector_b(A, b, g.PLaplacian(form.dΩ, uh2, source=-1.0), assem)
+    assert not all(np.array_equal(a0, c[2]) for a0, c in zip(v0, A.csr_arrays(values_only=True)))
+    A, b = g.assemble_matrix_and_vector_b(A, b, g.PLaplacian(form.dΩ, uh, source=-1.0), assem)
+    for a0, a1 in zip(v0, [c[2] for c in A.csr_arrays(values_only=True)]):
+        assert np.array_equal(a0, a1)
+    for x0, x1 in zip(b0, b.vector_partition):
+        assert np.array_equal(x0, x1)
+    assem.close()
+
+
+def test_newton_solution_kat():
+    """reference test/PLaplacianTests.jl:20-66: u = x+y (k = 1) on (0,4)^2, 4x4 cells, (2,2) parts, Newton from uh = 0;
+    sqrt(sum(∫ abs2(u - uh))) < 1e-9.  The linear solves are done on the host here (the reference uses `\\`)."""
+    u = lambda x: x[0] + x[1]
+    pr = build_problem((2, 2), (4, 4), 1, "boundary", u, "sub", domain=[0, 4, 0, 4])
+    n = pr.U.gids.indices[0].n_global
+    glob = np.zeros(n)
+    assem = None
+    for it in range(20):
+        uh = [glob[ids.l2g - 1] for ids in pr.U.gids.indices]
+        assem, form, A, b = _assemble(pr, uh, 0.0, assem=assem)       # f = -div sigma(grad u) = 0 for linear u
+        out_like = []
+        for M, r, c, bv in zip(A.matrix_partition, A.row_partition.indices, A.col_partition.indices, b.vector_partition):
+            out_like.append((M, r, c, bv))
+        import scipy.sparse as sp
+        rows, cols, vals = [], [], []
+        bg = np.zeros(n)
+        for M, r, c, bv in out_like:
+            M = M.tocoo(); keep = M.row < r.own_length
+            rows.append(r.l2g[M.row[keep]] - 1); cols.append(c.l2g[M.col[keep]] - 1); vals.append(M.data[keep])
+            bg[r.l2g[: r.own_length] - 1] += bv[: r.own_length]
+        Ag = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+        if np.linalg.norm(bg) < 1e-13:
+            break
+        glob = glob - spla.spsolve(Ag.tocsc(), bg)
+    assert it < 19
+    assert l2_error(pr, glob, u) < 1e-9
+    assem.close()

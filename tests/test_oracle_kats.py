@@ -140,3 +140,29 @@ def test_block_pipeline_reduces_to_single_field():
                 assert np.array_equal(u, w)
             assert np.array_equal(a["rows"]["l2g"], c["rows"]["l2g"]) and np.array_equal(a["cols"]["l2g"], c["cols"]["l2g"])
             assert np.array_equal(a["b"], c["b"])
+
+
+def test_state_dependent_forms_jacobian_is_the_derivative_of_the_residual():
+    """Oracle self-consistency for the forms of reference test/PLaplacianTests.jl:24-31: K(uh) = d r(uh) / d uh (central
+    differences), on a general (non-affine) quad cell; and r(u) = 0 for the linear exact solution with f = 0."""
+    from oracle import assembly_oracle as orc
+    import graft_import
+    g = graft_import.load()
+    ref = g.NCube(2).q2_ref_nodes()
+    X = np.array([[[0.0, 0.0], [1.1, 0.1], [-0.1, 0.9], [1.0, 1.2]]])
+    rng = np.random.default_rng(0)
+    uc = rng.uniform(-1, 1, (1, 9))
+    K, F = orc.integrate_cells(("plaplacian", uc), X, ref, 2, 1, 4, None)
+    eps = 1e-6
+    for j in range(9):
+        up, um = uc.copy(), uc.copy()
+        up[0, j] += eps; um[0, j] -= eps
+        Fp = orc.integrate_cells(("plaplacian", up), X, ref, 2, 1, 4, None)[1]
+        Fm = orc.integrate_cells(("plaplacian", um), X, ref, 2, 1, 4, None)[1]
+        assert np.allclose((Fp - Fm)[0] / (2 * eps), K[0, :, j], rtol=1e-6, atol=1e-8)
+    # linear u: sigma(grad u) is constant, its divergence vanishes: interior residual entries are zero (Q2 cell-interior node = 8)
+    Xa = np.array([[[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]])
+    lin = (ref[:, 0] + ref[:, 1])[None, :]
+    Fl = orc.integrate_cells(("plaplacian", lin), Xa, ref, 2, 1, 4, None)[1]
+    interior = int(np.flatnonzero(np.all(np.isclose(ref, 0.5), axis=1))[0])
+    assert abs(Fl[0, interior]) < 1e-13
