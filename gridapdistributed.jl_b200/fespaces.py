@@ -62,7 +62,11 @@ class LocalFESpace:
         face_keys_in_order = []
         for d in dims:
             mids = poly.face_mid[d]  # (nlf, D) in half units
-            keys = ((2 * ci)[:, None, :] + mids[None, :, :]) @ hstride  # (ncells, nlf)
+            hpos = (2 * ci)[:, None, :] + mids[None, :, :]
+            for dd in range(D):   # a locally periodic direction: the nodes of the far end ARE the nodes of the near end
+                if model.periodic_local[dd]:
+                    hpos[:, :, dd] = hpos[:, :, dd] % (2 * n[dd])
+            keys = hpos @ hstride  # (ncells, nlf)
             cell_node_keys[:, col : col + len(mids)] = keys
             col += len(mids)
             flat = keys.ravel()  # cell-major, local-face order
@@ -77,7 +81,7 @@ class LocalFESpace:
         # Dirichlet tagging from the GLOBAL position of each node
         hidx = np.stack([(all_keys // hstride[d]) % hn[d] for d in range(D)], axis=1)
         hidx_glob = hidx + 2 * model.cmin[None, :]
-        entity = boundary_entity_of_nodes(poly, hidx_glob, model.ncells_global)
+        entity = boundary_entity_of_nodes(poly, hidx_glob, model.ncells_global, model.no_boundary)
         tags = np.zeros(poly.num_entities + 1, dtype=bool)
         for t in _resolve_tags(dirichlet_tags, poly):
             tags[t] = True

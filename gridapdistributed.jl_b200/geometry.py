@@ -78,8 +78,13 @@ class NCube:
 class CartesianLocalModel:
     """The serial ``CartesianDiscreteModel(desc,cmin,cmax)`` of one part's local box."""
 
-    def __init__(self, D, origin, h, ncells_global, cmin, ncells_local, cell_owner, part):
+    def __init__(self, D, origin, h, ncells_global, cmin, ncells_local, cell_owner, part, periodic_local=None, no_boundary=None):
         self.D = D
+        # periodic_local[d]: the LOCAL model is periodic in direction d (periodic and not partitioned: the nodes of its two ends
+        # are identified); no_boundary[d]: direction d has no boundary at all (periodic, partitioned or not) -- reference
+        # Geometry.jl:413-459 (`remove_boundary`, local periodicity only in the directions that are not partitioned)
+        self.periodic_local = np.zeros(D, dtype=bool) if periodic_local is None else np.asarray(periodic_local, dtype=bool)
+        self.no_boundary = np.zeros(D, dtype=bool) if no_boundary is None else np.asarray(no_boundary, dtype=bool)
         self.origin = np.asarray(origin, dtype=np.float64)  # global origin
         self.h = np.asarray(h, dtype=np.float64)
         self.ncells_global = np.asarray(ncells_global, dtype=np.int64)
@@ -123,8 +128,9 @@ class CartesianLocalModel:
 class DistributedCartesianDiscreteModel:
     """``CartesianDiscreteModel(ranks, parts, domain, cells)`` (reference Geometry.jl:378-411)."""
 
-    def __init__(self, ranks, parts, domain, cells):
+    def __init__(self, ranks, parts, domain, cells, isperiodic=None):
         self.backend = ranks
+        self.isperiodic = tuple(bool(p) for p in isperiodic) if isperiodic is not None else tuple(False for _ in parts)
         self.parts = tuple(int(p) for p in parts)
         self.D = D = len(self.parts)
         assert len(cells) == D and len(domain) == 2 * D
@@ -150,13 +156,15 @@ class DistributedCartesianDiscreteModel:
         for d in range(D):
             p.append(r % self.parts[d] + 1)
             r //= self.parts[d]
-        own = [uniform_local_range(p[d], self.parts[d], self.cells[d]) for d in range(D)]
-        loc = [uniform_local_range(p[d], self.parts[d], self.cells[d], ghost=True) for d in range(D)]
+        # a periodic AND partitioned direction gets a ghost cell on either side that wraps around (Geometry.jl:436-449:
+        # local_range(...,ghost,global_isperiodic)); a periodic direction with one part is handled by the local model
+        wrap = [self.isperiodic[d] and self.parts[d] != 1 for d in range(D)]
+        loc = [uniform_local_range(p[d], self.parts[d], self.cells[d], ghost=True, periodic=wrap[d]) for d in range(D)]
         # per direction owner of every local index (PArraysExtras.jl:26-36)
         owners_d = []
         for d in range(D):
             bounds = [uniform_local_range(q, self.parts[d], self.cells[d]) for q in range(1, self.parts[d] + 1)]
-            idx = np.arange(loc[d][0], loc[d][1] + 1)
+            idx = (np.arange(loc[d][0], loc[d][1] + 1) - 1) % self.cells[d] + 1   # wrapped global index of every local index
             o = np.zeros(len(idx), dtype=np.int64)
             for q, (a, b) in enumerate(bounds):
                 o[(idx >= a) & (idx <= b)] = q + 1
@@ -171,12 +179,14 @@ class DistributedCartesianDiscreteModel:
         pstride, gstride = 1, 1
         for d in range(D):
             owner += (owners_d[d][ci[:, d]] - 1) * pstride
-            gid += (ci[:, d] + cmin[d]) * gstride
+            gid += ((ci[:, d] + cmin[d]) % self.cells[d]) * gstride
             pstride *= self.parts[d]
             gstride *= self.cells[d]
         owner = (owner + 1).astype(np.int32)
         gid = gid + 1
-        model = CartesianLocalModel(D, self.origin, self.h, self.cells, cmin, nloc, owner, part)
+        model = CartesianLocalModel(D, self.origin, self.h, self.cells, cmin, nloc, owner, part,
+                                    periodic_local=[self.isperiodic[d] and self.parts[d] == 1 for d in range(D)],
+                                    no_boundary=list(self.isperiodic))
         ids = LocalIndices(nglob, part, gid, owner)
         return model, ids
 
@@ -184,8 +194,9 @@ class DistributedCartesianDiscreteModel:
         return self.models
 
 
-def CartesianDiscreteModel(ranks, parts, domain, cells):
-    return DistributedCartesianDiscreteModel(ranks, parts, domain, cells)
+def CartesianDiscreteModel(ranks, parts, domain, cells, isperiodic=None):
+    """``CartesianDiscreteModel(ranks,parts,domain,cells;isperiodic=...)`` (reference Geometry.jl:378-459)."""
+    return DistributedCartesianDiscreteModel(ranks, parts, domain, cells, isperiodic)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -235,7 +246,7 @@ class Measure:
         self.degree = int(degree)
 
 
-def boundary_entity_of_nodes(poly: NCube, half_idx_global, ncells_global):
+def boundary_entity_of_nodes(poly: NCube, half_idx_global, ncells_global, no_boundary=None):
     """Entity id (Cartesian face-labeling tag, 1-based) of nodes given by GLOBAL half-cell indices.
 
     flag per direction: 0 = on the low boundary, 2 = on the high boundary, 1 = interior.  The
@@ -247,6 +258,8 @@ def boundary_entity_of_nodes(poly: NCube, half_idx_global, ncells_global):
     flag = np.ones(half_idx_global.shape, dtype=np.int64)
     flag[half_idx_global == 0] = 0
     flag[half_idx_global == n2[None, :]] = 2
+    if no_boundary is not None:   # periodic directions have no boundary
+        flag[:, np.asarray(no_boundary, dtype=bool)] = 1
     code = np.zeros(len(half_idx_global), dtype=np.int64)
     for d in range(D):
         code += flag[:, d] * 3**d

@@ -130,3 +130,56 @@ def neumann_cellvec_2d(pr, gfun, tags=(6, 8), quad_degree=4):
             F[sel] += np.einsum("q,c,qi,cq->ci", w1, length, phi, gq)
         out.append(F)
     return out
+
+
+def stokes_problem(parts, cells, strategy, ufun=None, domain=None):
+    pr = g.build_stokes_problem(parts, cells, strategy, ufun=ufun) if domain is None else _stokes_problem_on(parts, cells, strategy, ufun, domain)
+    return pr
+
+
+def _stokes_problem_on(parts, cells, strategy, ufun, domain):
+    D = len(cells)
+    pr = Problem()
+    pr.backend = g.DebugBackend(int(np.prod(parts)))
+    pr.model = g.CartesianDiscreteModel(pr.backend, parts, domain, cells)
+    pr.V = g.TestFESpace(pr.model, g.ReferenceFE("lagrangian", float, 2, ncomp=D), dirichlet_tags="boundary")
+    pr.Q = g.TestFESpace(pr.model, g.ReferenceFE("lagrangian", float, 1), dirichlet_tags=None)
+    pr.U = g.TrialFESpace(ufun, pr.V)
+    pr.P = g.TrialFESpace(None, pr.Q)
+    pr.strategy, pr.D = strategy, D
+    pr.trian = g.Triangulation(g.FullyAssembledRows(), pr.model) if strategy == "fully" else g.Triangulation(pr.model)
+    return pr
+
+
+def stokes_oracle(pr, nu, source, perturb=None, extra_p=None):
+    """The oracle's block pipeline on the Taylor-Hood Stokes forms; extra_p: per-part additive pressure cell vectors."""
+    nf = 2
+    spaces = [pr.U, pr.P]
+    dofs = [[orc.local_indices(i.n_global, i.part, i.l2g, i.l2o) for i in sp.gids.indices] for sp in spaces]
+    P = len(pr.model.models)
+    I = [[[None] * P for _ in range(nf)] for _ in range(nf)]
+    J = [[[None] * P for _ in range(nf)] for _ in range(nf)]
+    V = [[[None] * P for _ in range(nf)] for _ in range(nf)]
+    B = [[None] * P for _ in range(nf)]
+    T = [[None] * P for _ in range(nf)]
+    for k, m in enumerate(pr.model.models):
+        lids = pr.trian.cell_lids[k]
+        X = cell_coords(m, lids)
+        if perturb is not None:
+            X = perturb(m, lids, X)
+        su, sp_ = pr.U.spaces[k], pr.P.spaces[k]
+        Kuu, Kup, Kpu, Fu = orc.integrate_stokes_cells(X, su.ref_nodes, sp_.ref_nodes, 2, 1, 4, nu, source)
+        idu, idp = su.cell_dof_ids[lids - 1], sp_.cell_dof_ids[lids - 1]
+        Fp = np.zeros((len(lids), idp.shape[1])) if extra_p is None else np.array(extra_p[k], dtype=np.float64)
+        # lifting with the Dirichlet values of both trial fields (FESpaces.jl:703-715; the pressure has none here)
+        Fu = orc.lift_dirichlet(Kuu, Fu, idu, pr.U.dirichlet_values[k])
+        Fu = orc.lift_dirichlet(Kup, Fu, idp, pr.P.dirichlet_values[k])
+        Fp = orc.lift_dirichlet(Kpu, Fp, idu, pr.U.dirichlet_values[k])
+        masks = [(d[k]["l2o"] != d[k]["part"]) if pr.strategy == "fully" else None for d in dofs]
+        I[0][0][k], J[0][0][k], V[0][0][k], B[0][k], T[0][k] = orc.numeric_loop(idu, idu, Kuu, Fu, su.num_free_dofs, masks[0])
+        I[0][1][k], J[0][1][k], V[0][1][k], _, _ = orc.numeric_loop(idu, idp, Kup, None, su.num_free_dofs, masks[0])
+        I[1][0][k], J[1][0][k], V[1][0][k], B[1][k], T[1][k] = orc.numeric_loop(idp, idu, Kpu, Fp, sp_.num_free_dofs, masks[1])
+    I[1][1] = J[1][1] = V[1][1] = None  # the form does not touch the (p,p) block
+    return orc.create_from_nz_blocks(pr.strategy, I, J, V, B, T, dofs, dofs)
+
+

@@ -313,51 +313,7 @@ def test_general_cells_multi_part():
 
 
 # ---- block assembly (config 5: Taylor-Hood Stokes, BlockMultiFieldStyle) ------------------------------------------------
-def _stokes_problem(parts, cells, strategy):
-    from helpers import Problem
-    D = len(cells)
-    pr = Problem()
-    pr.backend = g.DebugBackend(int(np.prod(parts)))
-    pr.model = g.CartesianDiscreteModel(pr.backend, parts, sum(([0.0, 1.0] for _ in cells), []), cells)
-    pr.V = g.TestFESpace(pr.model, g.ReferenceFE("lagrangian", float, 2, ncomp=D), dirichlet_tags="boundary")
-    pr.Q = g.TestFESpace(pr.model, g.ReferenceFE("lagrangian", float, 1), dirichlet_tags=None)
-    pr.U = g.TrialFESpace(lambda x: np.stack([x[(d + 1) % D] * (1.0 - x[d]) + 0.25 * d for d in range(D)]), pr.V)
-    pr.P = g.TrialFESpace(None, pr.Q)
-    pr.strategy, pr.D = strategy, D
-    pr.trian = g.Triangulation(g.FullyAssembledRows(), pr.model) if strategy == "fully" else g.Triangulation(pr.model)
-    return pr
-
-
-def _stokes_oracle(pr, nu, source, perturb=None):
-    from helpers import cell_coords
-    nf = 2
-    spaces = [pr.U, pr.P]
-    dofs = [[orc.local_indices(i.n_global, i.part, i.l2g, i.l2o) for i in sp.gids.indices] for sp in spaces]
-    P = len(pr.model.models)
-    I = [[[None] * P for _ in range(nf)] for _ in range(nf)]
-    J = [[[None] * P for _ in range(nf)] for _ in range(nf)]
-    V = [[[None] * P for _ in range(nf)] for _ in range(nf)]
-    B = [[None] * P for _ in range(nf)]
-    T = [[None] * P for _ in range(nf)]
-    for k, m in enumerate(pr.model.models):
-        lids = pr.trian.cell_lids[k]
-        X = cell_coords(m, lids)
-        if perturb is not None:
-            X = perturb(m, lids, X)
-        su, sp_ = pr.U.spaces[k], pr.P.spaces[k]
-        Kuu, Kup, Kpu, Fu = orc.integrate_stokes_cells(X, su.ref_nodes, sp_.ref_nodes, 2, 1, 4, nu, source)
-        idu, idp = su.cell_dof_ids[lids - 1], sp_.cell_dof_ids[lids - 1]
-        Fp = np.zeros((len(lids), idp.shape[1]))
-        # lifting with the Dirichlet values of both trial fields (FESpaces.jl:703-715; the pressure has none here)
-        Fu = orc.lift_dirichlet(Kuu, Fu, idu, pr.U.dirichlet_values[k])
-        Fu = orc.lift_dirichlet(Kup, Fu, idp, pr.P.dirichlet_values[k])
-        Fp = orc.lift_dirichlet(Kpu, Fp, idu, pr.U.dirichlet_values[k])
-        masks = [(d[k]["l2o"] != d[k]["part"]) if pr.strategy == "fully" else None for d in dofs]
-        I[0][0][k], J[0][0][k], V[0][0][k], B[0][k], T[0][k] = orc.numeric_loop(idu, idu, Kuu, Fu, su.num_free_dofs, masks[0])
-        I[0][1][k], J[0][1][k], V[0][1][k], _, _ = orc.numeric_loop(idu, idp, Kup, None, su.num_free_dofs, masks[0])
-        I[1][0][k], J[1][0][k], V[1][0][k], B[1][k], T[1][k] = orc.numeric_loop(idp, idu, Kpu, Fp, sp_.num_free_dofs, masks[1])
-    I[1][1] = J[1][1] = V[1][1] = None  # the form does not touch the (p,p) block
-    return orc.create_from_nz_blocks(pr.strategy, I, J, V, B, T, dofs, dofs)
+from helpers import stokes_oracle as _stokes_oracle, stokes_problem as _stokes_problem  # noqa: E402
 
 
 @pytest.mark.parametrize("strategy", ["sub", "fully"])
@@ -510,4 +466,30 @@ def test_new_coordinates_and_dirichlet_values():
     A, b = g.assemble_matrix_and_vector_b(A, b, f, assem)
     out2, _ = oracle_assemble(pr2, ("poisson",), source=1.0)
     assert_matches_oracle(A, b, out2)
+    assem.close()
+
+
+# ---- periodic models (reference Geometry.jl:413-459, test/PeriodicBCsTests.jl) ---------------------------------------------
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+@pytest.mark.parametrize("parts", [(1, 1), (2, 2), (1, 4), (2, 3)])
+def test_periodic_model_matches_oracle_and_solves(parts, strategy):
+    """reference test/PeriodicBCsTests.jl:8-37 on the part grids of test/sequential/PeriodicBCsTests.jl:25-52: periodic in y,
+    Q2, u = sin(y+π/6) x.  Parity with the oracle (index maps bit-exact, values 1e-12) with the source as an FE function, and
+    the reference's solution bound with the device-assembled system."""
+    from test_oracle_kats import _periodic_problem
+    pr, u = _periodic_problem(parts, strategy, cells=(12, 12))
+    fun = lambda x: np.sin(x[1] + np.pi / 6) * x[0]
+    free = [fun(s.free_dof_coords.T) for s in pr.U.spaces]
+    dirv = [fun(s.dirichlet_dof_coords.T) if s.num_dirichlet_dofs else np.zeros(0) for s in pr.U.spaces]
+    nodal_cell = []
+    for k, s in enumerate(pr.U.spaces):
+        ids = s.cell_dof_ids[pr.trian.cell_lids[k] - 1]
+        d = dirv[k] if len(dirv[k]) else np.zeros(1)
+        nodal_cell.append(np.where(ids > 0, free[k][np.maximum(ids, 1) - 1], d[np.clip(-ids, 1, len(d)) - 1]))
+    out, _ = oracle_assemble(pr, ("poisson",), source=("nodal", nodal_cell))
+    assem, f, A, b = graft_assemble(pr, "poisson", source=("nodal", free, dirv))
+    assert_matches_oracle(A, b, out)
+    Ag, bg = gather_ours(A, b)
+    x = spla.spsolve(Ag.tocsc(), bg)
+    assert l2_error(pr, x, u) < 0.01   # 12x12 cells: (20/12)^3 x the reference bound 0.00122 for 20x20
     assem.close()

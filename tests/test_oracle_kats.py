@@ -166,3 +166,139 @@ def test_state_dependent_forms_jacobian_is_the_derivative_of_the_residual():
     Fl = orc.integrate_cells(("plaplacian", lin), Xa, ref, 2, 1, 4, None)[1]
     interior = int(np.flatnonzero(np.all(np.isclose(ref, 0.5), axis=1))[0])
     assert abs(Fl[0, interior]) < 1e-13
+
+
+@pytest.mark.parametrize("parts", [(1, 1), (1, 2), (2, 1), (2, 2)])
+def test_dof_count_kat_nonperiodic(parts):
+    """reference test/sequential/PeriodicBCsTests.jl:7-20, non-periodic column: Q1 on 4x4 cells without Dirichlet tags has 25
+    free dofs on every part grid -- pins generate_gids (FESpaces.jl:139-261), the producer of every index map."""
+    backend = g.DebugBackend(int(np.prod(parts)))
+    model = g.CartesianDiscreteModel(backend, parts, [0, 1, 0, 1], (4, 4))
+    V = g.FESpace(model, g.ReferenceFE("lagrangian", float, 1))
+    ids = V.gids.indices
+    assert all(i.n_global == 25 for i in ids)
+    owned = np.concatenate([i.l2g[i.l2o == i.part] for i in ids])
+    assert len(owned) == 25 and np.array_equal(np.sort(owned), np.arange(1, 26))   # every gid owned exactly once
+    # owners: a dof belongs to the highest part among the cells around it (FESpaces.jl:154-156)
+    for i in ids:
+        assert np.all((i.l2o >= 1) & (i.l2o <= int(np.prod(parts))))
+
+
+def test_measure_of_the_domain_kat():
+    """reference test/CellDataTests.jl:48: sum(∫(1)dΩ) ≈ 16 on (0,4)^2 with 4x4 cells, (2,2) parts (owned cells only): through
+    the oracle's quadrature, sum_cells sum_q w_q |det J_q| with degree 1."""
+    pr = build_problem((2, 2), (4, 4), 1, None, None, "sub", domain=[0, 4, 0, 4])
+    from helpers import cell_coords
+    tot = 0.0
+    for k, m in enumerate(pr.model.models):
+        X = cell_coords(m, pr.trian.cell_lids[k])
+        phi, dphi, w, xi = orc.reference_tables(2, 1, pr.U.spaces[k].ref_nodes, 1)
+        N, dN = orc.geometry_tables(2, xi)
+        J = np.einsum("cvd,qva->cqda", X, dN)
+        tot += float(np.einsum("q,cq->", w, np.abs(np.linalg.det(J))))
+    assert abs(tot - 16.0) < 1e-12
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+def test_stokes_solution_kat(strategy):
+    """Solution-level KAT of the block pipeline, after reference test/MultiFieldTests.jl:27-57,69-76 (domain (0,4)^2, 4x4 cells,
+    (2,2) parts, k = 2, u = ((x+y)^2, (x-y)^2), p = x+y - mean, f = -Δu + ∇p, g = ∇·u, BlockMultiFieldStyle): with the
+    Taylor-Hood pair Q2^2/Q1 the exact solution lies in the FE space, so the discrete solution reproduces it (the reference
+    checks l2 errors < 1e-9).  Pressure: continuous Q1 here (the reference uses P1-discontinuous + zero mean), fixed by its mean."""
+    from helpers import cell_coords, stokes_oracle, stokes_problem
+    import scipy.sparse as sp
+    u = lambda x: np.stack([(x[0] + x[1]) ** 2, (x[0] - x[1]) ** 2])
+    pfun = lambda x: x[0] + x[1] - 4.0
+    pr = stokes_problem((2, 2), (4, 4), strategy, ufun=u, domain=[0, 4, 0, 4])
+    # l((v,q)) = ∫ v⋅f - q*g with f = (-4 + 1, -4 + 1) constant and g = 4 y: the q*g term as pressure cell vectors
+    extra_p = []
+    for k, m in enumerate(pr.model.models):
+        lids = pr.trian.cell_lids[k]
+        X = cell_coords(m, lids)
+        phip, _, w, xi = orc.reference_tables(2, 1, pr.P.spaces[k].ref_nodes, 4)
+        N, dN = orc.geometry_tables(2, xi)
+        xq = np.einsum("qv,cvd->cqd", N, X)
+        wd = w[None, :] * np.abs(np.linalg.det(np.einsum("cvd,qva->cqda", X, dN)))
+        extra_p.append(-np.einsum("cq,qi,cq->ci", wd, phip, 4.0 * xq[:, :, 1]))
+    out = stokes_oracle(pr, 1.0, -3.0, extra_p=extra_p)
+    nu_, np_ = pr.U.gids.indices[0].n_global, pr.P.gids.indices[0].n_global
+    def gather_block(parts_out):
+        nr, nc = parts_out[0]["rows"]["n"], parts_out[0]["cols"]["n"]
+        rows, cols, vals, b = [], [], [], np.zeros(nr)
+        for p in parts_out:
+            rowptr, colind, val = p["csr"]
+            nown = len(p["rows"]["own_to_local"])
+            rid = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+            keep = rid < nown
+            rows.append(p["rows"]["l2g"][rid[keep]] - 1); cols.append(p["cols"]["l2g"][colind[keep]] - 1); vals.append(val[keep])
+            if p["b"] is not None:
+                b[p["rows"]["l2g"][:nown] - 1] += p["b"][:nown]
+        return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nr, nc)), b
+
+    blocks = {}
+    for (i, j) in ((0, 0), (0, 1), (1, 0)):
+        blocks[(i, j)], b = gather_block(out[i][j])
+        if j == 0:
+            blocks[("b", i)] = b
+    K = sp.bmat([[blocks[(0, 0)], blocks[(0, 1)]], [blocks[(1, 0)], None]], format="csr")
+    rhs = np.concatenate([blocks[("b", 0)], blocks[("b", 1)]])
+    # exact nodal values
+    ue, pe = np.zeros(nu_), np.zeros(np_)
+    for k in range(len(pr.model.models)):
+        su, sq = pr.U.spaces[k], pr.P.spaces[k]
+        iu, ip = pr.U.gids.indices[k], pr.P.gids.indices[k]
+        vals = u(su.free_dof_coords.T)
+        ue[iu.l2g - 1] = vals[su.free_dof_comp, np.arange(len(su.free_dof_comp))]
+        pe[ip.l2g - 1] = pfun(sq.free_dof_coords.T)
+    xe = np.concatenate([ue, pe])
+    assert np.abs(K @ xe - rhs).max() < 1e-10 * np.abs(rhs).max()       # the interpolant solves the discrete system
+    # and the system determines it (up to the pressure constant): solve with one pressure dof pinned
+    keep = np.arange(nu_ + np_ - 1)
+    x = np.zeros(nu_ + np_)
+    x[-1] = xe[-1]
+    x[keep] = spla.spsolve(K[keep][:, keep].tocsc(), rhs[keep] - K[keep][:, [nu_ + np_ - 1]].toarray().ravel() * xe[-1])
+    assert np.abs(x - xe).max() < 1e-9
+
+
+@pytest.mark.parametrize("parts", [(1, 1), (1, 2), (2, 1), (2, 2)])
+@pytest.mark.parametrize("isperiodic,ndofs", [((False, False), 25), ((False, True), 20), ((True, False), 20), ((True, True), 16)])
+def test_dof_count_kat_periodic(parts, isperiodic, ndofs):
+    """reference test/sequential/PeriodicBCsTests.jl:7-20: ndofss = [25,20,20,16] for the four periodicity patterns on every
+    part grid (periodic models: reference Geometry.jl:413-459)."""
+    backend = g.DebugBackend(int(np.prod(parts)))
+    model = g.CartesianDiscreteModel(backend, parts, [0, 1, 0, 1], (4, 4), isperiodic=isperiodic)
+    V = g.FESpace(model, g.ReferenceFE("lagrangian", float, 1))
+    assert all(i.n_global == ndofs for i in V.gids.indices)
+    owned = np.concatenate([i.l2g[i.l2o == i.part] for i in V.gids.indices])
+    assert np.array_equal(np.sort(owned), np.arange(1, ndofs + 1))
+
+
+def _periodic_problem(parts, strategy="sub", cells=(20, 20)):
+    from helpers import Problem
+    u = lambda x: np.sin(x[1] + np.pi / 6) * x[0]
+    pr = Problem()
+    pr.backend = g.DebugBackend(int(np.prod(parts)))
+    pr.domain = [0, 4, 0, 2 * np.pi]
+    pr.model = g.CartesianDiscreteModel(pr.backend, parts, pr.domain, cells, isperiodic=(False, True))
+    pr.reffe = g.ReferenceFE("lagrangian", float, 2)
+    pr.V = g.TestFESpace(pr.model, pr.reffe, dirichlet_tags="boundary")
+    pr.U = g.TrialFESpace(u, pr.V)
+    pr.strategy = strategy
+    pr.trian = g.Triangulation(g.FullyAssembledRows(), pr.model) if strategy == "fully" else g.Triangulation(pr.model)
+    pr.D, pr.order, pr.ncomp = 2, 2, 1
+    return pr, u
+
+
+@pytest.mark.parametrize("parts", [(1, 1), (2, 2), (1, 4), (2, 3)])
+def test_periodic_poisson_solution_kat(parts):
+    """reference test/PeriodicBCsTests.jl:8-37 (part grids of test/sequential/PeriodicBCsTests.jl:25-52): domain (0,4)x(0,2π),
+    20x20 cells, periodic in y, u = sin(y+π/6) x, f = -Δu, Q2, Dirichlet on the (remaining) boundary:
+    sqrt(sum(∫ abs2(u - uh))) < 0.00122."""
+    pr, u = _periodic_problem(parts)
+    f = lambda x: np.sin(x[1] + np.pi / 6) * x[0]          # -Δu
+    out, _ = oracle_assemble(pr, ("poisson",), source=f)
+    A, b = gather_global(out)
+    x = spla.spsolve(A.tocsc(), b)
+    err = l2_error(pr, x, u)
+    assert err < 0.00122
+    assert err > 1e-6   # a discretisation error, not an interpolation identity
