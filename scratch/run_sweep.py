@@ -9,6 +9,7 @@ from helpers import build_problem
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 pert = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+what = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 pr = build_problem((1, 1, 1), (cells,) * 3, 2, "boundary", lambda x: x[0] + x[1] + x[2], "sub")
 rng = np.random.default_rng(0)
 def perturb(m, xyz):
@@ -20,13 +21,13 @@ form = g.Poisson(g.Measure(pr.trian, 4), source=1.0)
 assem._set_form(form); assem._symbolic(form)
 lib, comm = assem.comm.lib, assem.comm.handle
 for _ in range(2):
-    L.check(lib.graft_numeric(comm, 3))
+    L.check(lib.graft_numeric(comm, what))
 L.check(lib.graft_sync(comm))
 ts = []
 for _ in range(steps):
-    L.check(lib.graft_numeric(comm, 3)); L.check(lib.graft_sync(comm))
+    L.check(lib.graft_numeric(comm, what)); L.check(lib.graft_sync(comm))
     ts.append(assem.timers()[0][L.T_NUMERIC])
 st = assem.stats()[0]
-print({"cells": cells, "route": st["path"], "ms": float(np.min(ts)), "ms_mean": float(np.mean(ts)), "nnz": st["nnz"],
+print({"what": what, "cells": cells, "route": st["path"], "ms": float(np.min(ts)), "ms_mean": float(np.mean(ts)), "nnz": st["nnz"],
        "GBps_alg": (8 * st["nnz"] + 8 * st["nrows"] + 108 * st["ncells"] + 24 * (cells + 1) ** 3) / (np.min(ts) * 1e-3) / 1e9})
 assem.close()
