@@ -379,13 +379,17 @@ __device__ __forceinline__ void sw_bar_arrive(int id, int n) { asm volatile("bar
 // The address-table entries of all the row's slots are requested first (rows of up to 128 nnz: one load latency per row).
 template <int NE>
 __device__ __forceinline__ double sw_gather(const uint4 w, const uint32_t* bt) {
-  double v = 0.0;
+  double l[NE];
 #pragma unroll
   for (int t = 0; t < NE; ++t) {
     const unsigned word = t < 2 ? w.x : (t < 4 ? w.y : (t < 6 ? w.z : w.w));
-    v += sw_lds(bt[t] + ((t & 1) ? (word >> 16) : (word & 0xffffu)));
+    l[t] = sw_lds(bt[t] + ((t & 1) ? (word >> 16) : (word & 0xffffu)));
   }
-  return v;
+  // pairwise sum in a fixed order (the same for every assembly: bitwise repeatable)
+  if (NE == 1) return l[0];
+  if (NE == 2) return l[0] + l[1];
+  if (NE == 4) return (l[0] + l[1]) + (l[2] + l[3]);
+  return ((l[0] + l[1]) + (l[2] + l[3])) + ((l[NE > 4 ? 4 : 0] + l[NE > 5 ? 5 : 0]) + (l[NE > 6 ? 6 : 0] + l[NE > 7 ? 7 : 0]));
 }
 template <int NE>
 __device__ __forceinline__ void sw_emit_row(const uint4* __restrict__ inv, int len, int lane, const uint32_t* bt, double* __restrict__ out) {
@@ -549,6 +553,12 @@ __global__ void __launch_bounds__(SW_NT, 1) sweep_q2_kernel(SweepArgs a, int wha
           T22[q2] = x0[0] * g0 + x0[1] * g1 + x0[2] * g2;
         }
       }
+      if (x < xlast)   // the records of the next layer: on their way to L2 while this layer is integrated
+        for (int it = tid; it < ncs * 12; it += SW_NI) {
+          const int cs = it / 12, ln = it - cs * 12;
+          const int64_t k = x + 1 + (int64_t)n0 * (cs_y[cs] + (int64_t)n1 * cs_z[cs]);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.georec + k * SW_GEO) + 128 * ln));
+        }
       SW_TICK(1, 0);
       if (x - xbeg >= 2) sw_bar_sync(SW_BAR_EMPTY + b, SW_NT);   // the emitters are done with this buffer (layer x - 2)
       SW_TICK(0, 0);
@@ -694,21 +704,18 @@ __global__ void __launch_bounds__(SW_NT, 1) sweep_q2_kernel(SweepArgs a, int wha
             if (ok) { mymask |= 1 << e; if (ox || first < 0 || !(first & 1)) first = e; }
           }
           {
-            const unsigned short z0 = (unsigned short)(b * SW_NCS * (SW_SLOT / 2));   // beyond the last entry: cell 0 of the buffer (its zero)
-            unsigned short hb[8] = {z0, z0, z0, z0, z0, z0, z0, z0};
+            const unsigned z0 = (unsigned)(b * SW_NCS * (SW_SLOT / 2));   // beyond the last entry: cell 0 of the buffer (its zero)
+            tbase[et] = make_uint4(z0 | (z0 << 16), z0 | (z0 << 16), z0 | (z0 << 16), z0 | (z0 << 16));
+            unsigned short* hb = reinterpret_cast<unsigned short*>(tbase + et);
             int t = 0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int cs = t_cs[e >> 1];
-              const bool ok = (mymask >> e) & 1;
-              const unsigned short v = (unsigned short)((e & 1) ? (b * SW_NCS + cs) * (SW_SLOT / 2) : 2 * SW_NCS * (SW_SLOT / 2) + cs * (SW_FSLOT / 2));
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if (ok && t == u) hb[u] = v;
-              t += ok ? 1 : 0;
+              if ((mymask >> e) & 1) {
+                hb[t] = (unsigned short)((e & 1) ? (b * SW_NCS + cs) * (SW_SLOT / 2) : 2 * SW_NCS * (SW_SLOT / 2) + cs * (SW_FSLOT / 2));
+                ++t;
+              }
             }
-            tbase[et] = make_uint4(hb[0] | ((unsigned)hb[1] << 16), hb[2] | ((unsigned)hb[3] << 16), hb[4] | ((unsigned)hb[5] << 16),
-                                   hb[6] | ((unsigned)hb[7] << 16));
           }
           if (first >= 0) {
             const int ox = first & 1, oy = (first >> 1) & 1, oz = first >> 2;
