@@ -12,6 +12,7 @@ from .geometry import (CartesianDiscreteModel, Triangulation, Measure, SubAssemb
 from .fespaces import ReferenceFE, lagrangian, FESpace, TestFESpace, TrialFESpace, generate_gids
 from .assembly import (SparseMatrixAssembler, GraftSparseMatrixAssembler, assemble_matrix_and_vector, assemble_matrix,
                        assemble_vector, allocate_matrix_and_vector, assemble_matrix_and_vector_b, AffineFEOperator,
-                       PSparseMatrix, PVector, BlockPMatrix, BlockPVector, mul, cg, pvector_on_cols, pvector_on_rows, Poisson, Mass, LinearElasticity, StokesTH, PLaplacian)
+                       PSparseMatrix, PVector, BlockPMatrix, BlockPVector, mul, cg, pvector_on_cols, pvector_on_rows, Poisson, Mass, LinearElasticity, StokesTH, PLaplacian,
+                       CellArrays, collect_cell_matrix_and_vector)
 from .problems import build_problem, build_stokes_problem, vertex_perturbation, interior_vertex_mask
 from . import libgraft

@@ -83,6 +83,30 @@ class PLaplacian(GraftForm):
         self.uh = uh
 
 
+class CellArrays(GraftForm):
+    """Hook 1, "bring your own cell arrays": the ``data`` of ``collect_cell_matrix_and_vector(trial,test,a,l)`` (reference
+    FESpaces.jl:691-743) already evaluated -- ``mats[(i,j)][part]``: (ncells, nd_i, nd_j) cell matrices of block (i,j) (a
+    missing key = a block the form does not touch, the ``touched`` of Gridap's ArrayBlock), ``vecs[i][part]``: (ncells, nd_i)
+    Dirichlet-lifted cell vectors of block row i.  ``assemble_matrix_and_vector(data, assem)`` is then the reference's
+    ``assemble_matrix_and_vector(assem, data)`` (FESpaces.jl:763-798; blocks: MultiField.jl:473-560)."""
+
+    form_id = L.FORM_USER
+
+    def __init__(self, dΩ, mats, vecs=None):
+        super().__init__(dΩ, None, None)
+        if not isinstance(mats, dict):
+            mats = {(0, 0): mats}
+        if vecs is not None and not isinstance(vecs, dict):
+            vecs = {0: vecs}
+        self.mats, self.vecs = mats, (vecs or {})
+        nf = 1 + max(max(i, j) for i, j in mats)
+        self.params = tuple(1.0 if (i, j) in mats else 0.0 for i in range(nf) for j in range(nf))
+
+
+def collect_cell_matrix_and_vector(dΩ, mats, vecs=None):
+    return CellArrays(dΩ, mats, vecs)
+
+
 # ----------------------------------------------------------------------------------------------
 # communicator handling: DebugBackend -> local comm, DistBackend -> NCCL comm
 # ----------------------------------------------------------------------------------------------
@@ -321,7 +345,7 @@ class GraftSparseMatrixAssembler:
         return PRange(self.backend, idx)
 
     def _symbolic(self, form):
-        key = (form.form_id == L.FORM_STOKES, id(form.dΩ.trian), self.strategy.code)
+        key = (form.form_id == L.FORM_STOKES, form.params if form.form_id == L.FORM_USER else None, id(form.dΩ.trian), self.strategy.code)
         if self._symbolic_key == key:
             return
         L.check(self.comm.lib.graft_symbolic(self.comm.handle, self.strategy.code, self.index_base))
@@ -331,10 +355,32 @@ class GraftSparseMatrixAssembler:
         self.brows = [self._prange(2, f) for f in range(nf)]
         self._symbolic_key = key
 
-    def _numeric(self, what):
+    def _numeric(self, what, form=None):
         if what & 1:
             self._matrix_generation += 1
+        if isinstance(form, CellArrays):
+            return self._scatter(form, what)
         L.check(self.comm.lib.graft_numeric(self.comm.handle, what))
+
+    def _scatter(self, data, what):
+        """graft_scatter_cellmats block by block; the vector of block row i travels with the first block of that row."""
+        lib = self.comm.lib
+        keep = []
+
+        def per_part(arrs):
+            a = [np.ascontiguousarray(x, dtype=np.float64) for x in arrs]
+            keep.append(a)
+            return L.ptr_array(a)
+
+        done = set()
+        for (i, j) in sorted(data.mats):
+            mats = per_part(data.mats[(i, j)]) if what & 1 else None
+            vecs = None
+            if (what & 2) and i in data.vecs and i not in done:
+                vecs = per_part(data.vecs[i])
+                done.add(i)
+            if mats is not None or vecs is not None:
+                L.check(lib.graft_scatter_cellmats(self.comm.handle, i, j, mats, vecs))
 
     def _wrap(self):
         nf = len(self.trials)
@@ -389,7 +435,7 @@ def assemble_matrix_and_vector(form, assem):
     _check_triangulation(form, assem)
     assem._set_form(form)
     assem._symbolic(form)
-    assem._numeric(3)
+    assem._numeric(3, form)
     return assem._wrap(), assem._vectors()
 
 
@@ -397,7 +443,7 @@ def assemble_matrix(form, assem):
     _check_triangulation(form, assem)
     assem._set_form(form)
     assem._symbolic(form)
-    assem._numeric(1)
+    assem._numeric(1, form)
     return assem._wrap()
 
 
@@ -405,7 +451,7 @@ def assemble_vector(form, assem):
     _check_triangulation(form, assem)
     assem._set_form(form)
     assem._symbolic(form)
-    assem._numeric(2)  # vector only: the matrix values of this assembler are left alone (the lifting evaluates what it needs)
+    assem._numeric(2, form)  # vector only: the matrix values of this assembler are left alone (the lifting evaluates what it needs)
     return assem._vectors()
 
 
@@ -422,7 +468,7 @@ def assemble_matrix_and_vector_b(A, b, form, assem):
     sparsity, index sets and exchange plans are reused; bitwise repeatable."""
     assem._set_form(form)
     assem._symbolic(form)
-    assem._numeric(3)
+    assem._numeric(3, form)
     mats = [A] if isinstance(A, PSparseMatrix) else [m for row in A for m in row]
     for m in mats:
         m.generation = assem._matrix_generation        # A is the matrix being re-assembled: its handle stays valid

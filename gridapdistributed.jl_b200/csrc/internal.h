@@ -269,7 +269,8 @@ struct SweepPlan {
 
 struct Form {
   int id = 0;
-  double params[8] = {0};
+  double params[16] = {0};
+  int nparams = 0;
   int quad_degree = 0;
 };
 

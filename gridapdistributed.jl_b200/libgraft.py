@@ -61,7 +61,7 @@ SIGNATURES = {
 _RESTYPES = {"graft_last_error": C.c_char_p}
 
 T_SYMBOLIC, T_INTEGRATE, T_SCATTER, T_EXCHANGE, T_NUMERIC, T_SPMV, T_CG, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
-FORM_POISSON, FORM_MASS, FORM_ELASTICITY, FORM_STOKES, FORM_PLAPLACIAN = 1, 2, 3, 4, 5
+FORM_POISSON, FORM_MASS, FORM_ELASTICITY, FORM_STOKES, FORM_PLAPLACIAN, FORM_USER = 1, 2, 3, 4, 5, 6
 SOURCE_NONE, SOURCE_CONST, SOURCE_NODAL = 0, 1, 2
 
 

@@ -183,3 +183,34 @@ def stokes_oracle(pr, nu, source, perturb=None, extra_p=None):
     return orc.create_from_nz_blocks(pr.strategy, I, J, V, B, T, dofs, dofs)
 
 
+
+
+def block_oracle_from_cell_arrays(pr, spaces, mats, vecs):
+    """The oracle's block pipeline (numeric_loop per block + create_from_nz_blocks) on caller-supplied cell arrays:
+    mats[(i,j)][part] (ncells, nd_i, nd_j) -- a missing key is a block the form does not touch --, vecs[i][part]."""
+    nf = len(spaces)
+    dofs = [[orc.local_indices(i.n_global, i.part, i.l2g, i.l2o) for i in sp.gids.indices] for sp in spaces]
+    P = len(pr.model.models)
+    I = [[[None] * P if (i, j) in mats else None for j in range(nf)] for i in range(nf)]
+    J = [[[None] * P if (i, j) in mats else None for j in range(nf)] for i in range(nf)]
+    V = [[[None] * P if (i, j) in mats else None for j in range(nf)] for i in range(nf)]
+    B = [[None] * P for _ in range(nf)]
+    T = [[None] * P for _ in range(nf)]
+    for k in range(P):
+        lids = pr.trian.cell_lids[k]
+        ids = [sp.spaces[k].cell_dof_ids[lids - 1] for sp in spaces]
+        masks = [(d[k]["l2o"] != d[k]["part"]) if pr.strategy == "fully" else None for d in dofs]
+        for i in range(nf):
+            first = True
+            for j in range(nf):
+                if (i, j) not in mats:
+                    continue
+                F = vecs[i][k] if (first and i in vecs) else None
+                I[i][j][k], J[i][j][k], V[i][j][k], bb, tt = orc.numeric_loop(ids[i], ids[j], mats[(i, j)][k], F, spaces[i].spaces[k].num_free_dofs,
+                                                                               masks[i])
+                if first:
+                    B[i][k], T[i][k] = bb, tt
+                first = False
+    if not vecs:
+        B = None
+    return orc.create_from_nz_blocks(pr.strategy, I, J, V, B, T, dofs, dofs)

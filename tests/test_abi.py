@@ -67,3 +67,41 @@ def test_product_path_never_touches_the_oracle():
     fn = bench.index("def cpu_reference_run")
     fn_end = bench.index("\ndef ", fn + 1)
     assert uses and all(fn < u < fn_end for u in uses)
+
+
+def _abi_driver():
+    import __graft_entry__ as entry
+
+    return entry.build_abi_driver()
+
+
+def test_abi_driver_links_against_the_library():
+    """tests/abi_driver.c (the ccall sequence of julia/GraftAssembly.jl in plain C) compiles against include/graft.h alone and
+    resolves every symbol it uses from libgraft.so; `--link` stops before the first GPU call."""
+    import subprocess
+
+    out = subprocess.run([_abi_driver(), "--link"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "link ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_julia_shim_binds_only_declared_symbols():
+    """Every `:graft_*` symbol the Julia shim ccalls is declared in include/graft.h, and the shim covers hook 1 and the blocks."""
+    txt = open(os.path.join(ROOT, "julia", "GraftAssembly.jl")).read()
+    used = set(re.findall(r"\(:(graft_[a-z0-9_]+),\s*libgraft\)", txt))
+    syms = set(header_symbols())
+    assert used and used <= syms, used - syms
+    for must in ("graft_scatter_cellmats", "graft_symbolic", "graft_numeric", "graft_spmv", "graft_csr_get", "graft_prange_get"):
+        assert must in used
+    # the C driver performs the same sequence
+    drv = open(os.path.join(ROOT, "tests", "abi_driver.c")).read()
+    drv_used = set(re.findall(r"\b(graft_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", drv, flags=re.S)))
+    assert {"graft_scatter_cellmats", "graft_symbolic", "graft_numeric", "graft_spmv", "graft_cg", "graft_csr_get"} <= drv_used <= syms
+
+
+@pytest.mark.gpu
+def test_abi_driver_runs_the_shim_sequence_on_the_gpu():
+    import subprocess
+
+    for n in ("12", "3", "40"):
+        out = subprocess.run([_abi_driver(), n], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "abi_driver: ok" in out.stdout, out.stdout + out.stderr

@@ -493,3 +493,34 @@ def test_periodic_model_matches_oracle_and_solves(parts, strategy):
     x = spla.spsolve(Ag.tocsc(), bg)
     assert l2_error(pr, x, u) < 0.01   # 12x12 cells: (20/12)^3 x the reference bound 0.00122 for 20x20
     assem.close()
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+@pytest.mark.parametrize("parts,cells", [((2, 2), (4, 4)), ((2, 1, 2), (4, 2, 4)), ((3, 1), (6, 2))])
+@pytest.mark.parametrize("coupling", ["full", "no_00"])
+def test_hook1_coupled_blocks_match_oracle(parts, cells, strategy, coupling):
+    # hook 1 with a block system: the reference's assemble_matrix_and_vector(assem, data) for MultiField data
+    # (FESpaces.jl:763-798, MultiField.jl:473-560) on caller-supplied cell arrays; every block of a fully coupled 2 x 2 form
+    from helpers import block_oracle_from_cell_arrays
+
+    pr = _stokes_problem(parts, cells, strategy, ufun=lambda x: np.stack([x[0] - x[1]] * len(cells)))
+    spaces = [pr.U, pr.P]
+    rng = np.random.default_rng(11)
+    keys = [(0, 0), (0, 1), (1, 0), (1, 1)] if coupling == "full" else [(0, 1), (1, 0), (1, 1)]
+    nds = [sp.spaces[0].cell_dof_ids.shape[1] for sp in spaces]
+    mats = {(i, j): [rng.uniform(-1, 1, (len(l), nds[i], nds[j])) for l in pr.trian.cell_lids] for (i, j) in keys}
+    vecs = {i: [rng.uniform(-1, 1, (len(l), nds[i])) for l in pr.trian.cell_lids] for i in range(2)}
+    out = block_oracle_from_cell_arrays(pr, spaces, mats, vecs)
+    st = g.FullyAssembledRows() if strategy == "fully" else g.SubAssembledRows()
+    assem = g.SparseMatrixAssembler([pr.U, pr.P], [pr.V, pr.Q], st)
+    data = g.collect_cell_matrix_and_vector(g.Measure(pr.trian, 4), mats, vecs)
+    A, b = g.assemble_matrix_and_vector(data, assem)
+    for i in range(2):
+        first = min(j for (ii, j) in keys if ii == i)
+        for j in range(2):
+            if (i, j) in mats:
+                assert_matches_oracle(A[i][j], b[i], out[i][j], check_b=(j == first))
+    with pytest.raises(g.libgraft.GraftError):   # a pattern-only form has no integrand
+        L = g.libgraft
+        L.check(assem.comm.lib.graft_numeric(assem.comm.handle, 3))
+    assem.close()
