@@ -5,6 +5,8 @@
 #include "internal.h"
 
 int64_t g_bytes_allocated = 0;
+thread_local cudaStream_t g_pool_stream = nullptr;
+thread_local bool g_pool_on = false;
 static thread_local std::string g_last_error;
 
 void graft_throw(const char* fmt, ...) {

@@ -37,6 +37,33 @@ struct GraftError : std::runtime_error {
 // device buffer
 // ------------------------------------------------------------------------------------------------
 extern int64_t g_bytes_allocated;
+// Stream-ordered allocation scope (symbolic phase, one part per process): while g_pool_stream is set, DevBuf takes its memory from
+// the device's default memory pool on that stream (cudaMallocAsync) and gives it back to the pool (cudaFreeAsync) -- the dozens of
+// short-lived work arrays of the phase then cost no cudaMalloc / cudaFree round trips.  Outside the scope a pooled buffer is freed
+// with cudaFree (legal for pool memory; synchronises like before).
+extern thread_local cudaStream_t g_pool_stream;
+extern thread_local bool g_pool_on;
+struct PoolScope {
+  bool mine = false;
+  int device = 0;
+  PoolScope(bool enable, int dev, cudaStream_t s) : device(dev) {
+    if (!enable || g_pool_on) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) { cudaGetLastError(); return; }
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    g_pool_on = true; g_pool_stream = s; mine = true;
+  }
+  ~PoolScope() {
+    if (!mine) return;
+    g_pool_on = false; g_pool_stream = nullptr;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      cudaStreamSynchronize(nullptr);
+      cudaMemPoolTrimTo(pool, 0);   // what the phase no longer uses goes back to the driver (cudaMalloc users see it again)
+    }
+  }
+};
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -44,20 +71,30 @@ struct DevBuf {
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  bool pooled = false;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pooled(o.pooled) { o.p = nullptr; o.n = 0; o.pooled = false; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; pooled = o.pooled; o.p = nullptr; o.n = 0; o.pooled = false; }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) { cudaFree(p); g_bytes_allocated -= n * (int64_t)sizeof(T); }
-    p = nullptr; n = 0;
+    if (p) {
+      if (pooled && g_pool_on) cudaFreeAsync(p, g_pool_stream);
+      else cudaFree(p);
+      g_bytes_allocated -= n * (int64_t)sizeof(T);
+    }
+    p = nullptr; n = 0; pooled = false;
   }
   void alloc(int64_t count) {
     release();
     if (count > 0) {
-      CUDA_CHECK(cudaMalloc((void**)&p, (size_t)count * sizeof(T)));
+      if (g_pool_on) {
+        CUDA_CHECK(cudaMallocAsync((void**)&p, (size_t)count * sizeof(T), g_pool_stream));
+        pooled = true;
+      } else {
+        CUDA_CHECK(cudaMalloc((void**)&p, (size_t)count * sizeof(T)));
+      }
       g_bytes_allocated += count * (int64_t)sizeof(T);
     }
     n = count;
