@@ -552,15 +552,15 @@ def main():
         gp = routes.get("hex_nodes_perturbed", {})
         if "ms_per_step" in gp and args.form == "poisson":
             # algorithmic flops of the general-cell integration: 2 nq (D nd) nd = 118 098 per cell (dense B^T D B); the
-            # sum-factorised kernel executes 2 x 11 664 + geometry per cell
+            # sum-factorised kernels execute 2 x 11 664 + geometry per cell
             fl_alg, fl_exec = 118098.0 * st1["ncells"], (2 * 11664.0 + 27 * 150.0) * st1["ncells"]
             general = {"value": gp["nnz_per_s"], "unit": "nnz/s", "ms_per_step": gp["ms_per_step"], "route": gp["route"],
                        "ms_per_step_geometry_records_kept": gp.get("ms_per_step_geometry_records_kept"),
-                       "kernel": "sweep_geom_kernel+sweep_q2_kernel" if gp["route"] == "fused-sweep" else "integrate_small_kernel+gather_direct_kernel",
+                       "kernel": {"fused-sweep": "sweep_geom_kernel+sweep_q2_kernel", "sumfact-gather": "integrate_sumfact_q2_kernel+gather_direct_kernel"}.get(gp["route"], "integrate_small_kernel+gather_direct_kernel"),
                        "config": "same workload, mesh as node coordinates moved by <= 0.1 h (general trilinear hexes, per-cell Jacobians at 27 points)",
                        "roofline": {"bound": "hbm", "achieved": B_num / (gp["ms_per_step"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": gp["frac_of_hbm_peak"],
-                                    "traffic": traffic_of("sweep_geom_kernel+sweep_q2_kernel" if gp["route"] == "fused-sweep" else "integrate_small_kernel+gather_direct_kernel"),
+                                    "traffic": traffic_of({"fused-sweep": "sweep_geom_kernel+sweep_q2_kernel", "sumfact-gather": "integrate_sumfact_q2_kernel+gather_direct_kernel"}.get(gp["route"], "integrate_small_kernel+gather_direct_kernel")),
                                     "algorithmic_bytes_per_launch": B_num},
                        "fp64": {"algorithmic_tflops": fl_alg / (gp["ms_per_step"] * 1e-3) / 1e12, "executed_tflops": fl_exec / (gp["ms_per_step"] * 1e-3) / 1e12,
                                 "peak_tflops": FP64_PEAK_TFLOPS, "peak_source": "profiles/r2_fp64_peak.jsonl (DFMA/DMMA microbenchmark on this pool)"},

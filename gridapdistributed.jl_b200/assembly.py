@@ -413,7 +413,7 @@ class GraftSparseMatrixAssembler:
             s = np.zeros(8, dtype=np.int64)
             L.check(self.comm.lib.graft_stats_get(ctx, L.ptr(s)))
             out.append(dict(ncells=int(s[0]), ncoo=int(s[1]), nnz=int(s[2]), nrows=int(s[3]), ncols=int(s[4]), launches=int(s[5]),
-                            bytes_dev=int(s[6]), path={0: "none", 1: "unfused", 2: "fused-affine", 3: "fused-sweep"}[int(s[7])]))
+                            bytes_dev=int(s[6]), path={0: "none", 1: "unfused", 2: "fused-affine", 3: "fused-sweep", 4: "sumfact-gather"}[int(s[7])]))
         return out
 
 

@@ -268,7 +268,7 @@ void numeric_phase(graft_comm* c, int what) {
           vec_done = vec_done || with_vec;
         }
       }
-      x->last_path = 1;
+      x->last_path = x->sumfact_used ? 4 : 1;
     }
     CUDA_CHECK(cudaEventRecord(x->tev[2], s));
   }

@@ -26,8 +26,8 @@ L.check(lib.graft_sync(comm))
 ts = []
 for _ in range(steps):
     L.check(lib.graft_numeric(comm, what)); L.check(lib.graft_sync(comm))
-    ts.append(assem.timers()[0][L.T_NUMERIC])
+    ts.append(assem.timers()[0][L.T_NUMERIC]); ph = (float(assem.timers()[0][L.T_INTEGRATE]), float(assem.timers()[0][L.T_SCATTER]))
 st = assem.stats()[0]
-print({"what": what, "cells": cells, "route": st["path"], "ms": float(np.min(ts)), "ms_mean": float(np.mean(ts)), "nnz": st["nnz"],
+print({"what": what, "cells": cells, "route": st["path"], "ms": float(np.min(ts)), "ms_mean": float(np.mean(ts)), "nnz": st["nnz"], "all_ms": [round(float(t), 2) for t in ts], "integrate_scatter_ms_last": ph,
        "GBps_alg": (8 * st["nnz"] + 8 * st["nrows"] + 108 * st["ncells"] + 24 * (cells + 1) ** 3) / (np.min(ts) * 1e-3) / 1e9})
 assem.close()

@@ -44,7 +44,7 @@ def main():
         form = g.Poisson(g.Measure(pr.trian, 4), source=1.0)
         A, b = g.assemble_matrix_and_vector(form, assem)
         if geometry == "perturbed":
-            assert assem.stats()[0]["path"] == "fused-sweep"
+            assert assem.stats()[0]["path"] == "sumfact-gather"
         for rep in range(2):  # second pass: re-assembly (values only)
             p = out[rank]
             assert_same_prange(A.row_partition.indices[0], p["rows"], "rows")
