@@ -439,7 +439,8 @@ def main():
     peak, peak_src = measured_peak()
     route = st1["path"]
     dominant = {("fused-affine", "cartesian"): "stream_groups_kernel", ("fused-affine", "hex"): "gemm_rows_kernel",
-                ("fused-sweep", "hex"): "sweep_q2_kernel", ("fused-sweep", "perturbed"): "sweep_q2_kernel"}.get(
+                ("fused-sweep", "hex"): "sweep_q2_kernel", ("fused-sweep", "perturbed"): "sweep_q2_kernel",
+                ("sumfact-gather", "perturbed"): "integrate_sumfact_q2_kernel+gather_direct_kernel"}.get(
         (route, args.geometry), "integrate_small_kernel+gather_direct_kernel" if args.form == "poisson" else "integrate_cells_mma_kernel+gather_direct_kernel")
     achieved = B_num / (ms_per_step * 1e-3) / 1e9
 
