@@ -498,8 +498,10 @@ def main():
     roofline_symbolic = {"bound": "hbm", "achieved": B_sym / (t_sym * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": B_sym / (t_sym * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes": B_sym, "ms": t_sym,
                          "note": "B_sym = 4 nnz + 4 (nrows + 1) per part; first symbolic phase of the process (device time, max over ranks; includes growing "
-                                 "the memory pool).  Not bandwidth bound: the per-row duplicate elimination (row_unique_kernel, two passes) is 80 % of "
-                                 "its kernel time, see profiles/r2_launches_symbolic.csv"}
+                                 "the memory pool: 15 GB of device allocations, which are several times slower inside this process -- torch context "
+                                 "present -- than in a bare process: 178-266 ms first call, 174 ms repeated, scratch/run_symbolic.py).  Not bandwidth "
+                                 "bound: the kernels take 132 ms, of which the per-row duplicate elimination (row_unique_kernel, two passes) is 80 %, "
+                                 "see profiles/r2_launches_symbolic.csv"}
 
     # ---- Jacobi-CG on top of mul!: a fixed number of iterations on the assembled system ----------------
     cg = None
