@@ -8,7 +8,7 @@ There is no CPU fallback: without the library or a GPU the assembly calls raise.
 """
 from .parrays import DebugBackend, DistBackend, with_debug, with_dist, PRange, LocalIndices, OwnAndGhostIndices
 from .geometry import (CartesianDiscreteModel, Triangulation, Measure, SubAssembledRows,
-                       FullyAssembledRows, NCube)
+                       FullyAssembledRows, NCube, Boundary, facet_points)
 from .fespaces import ReferenceFE, lagrangian, FESpace, TestFESpace, TrialFESpace, generate_gids
 from .assembly import (SparseMatrixAssembler, GraftSparseMatrixAssembler, assemble_matrix_and_vector, assemble_matrix,
                        assemble_vector, allocate_matrix_and_vector, assemble_matrix_and_vector_b, AffineFEOperator,

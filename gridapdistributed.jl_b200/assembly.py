@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import libgraft as L
-from .geometry import FullyAssembledRows, Measure, SubAssembledRows
+from .geometry import FullyAssembledRows, Measure, SubAssembledRows, facet_points
 from .parrays import OwnAndGhostIndices, PRange
 
 # ----------------------------------------------------------------------------------------------
@@ -33,10 +33,14 @@ class GraftForm:
     form_id = 0
     params: tuple = ()
 
-    def __init__(self, dΩ: Measure, source=None, extra_cellvec=None):
+    def __init__(self, dΩ: Measure, source=None, extra_cellvec=None, neumann=None):
         self.dΩ = dΩ
         self.source = source  # None | float | sequence(ncomp) | ("nodal", free_values_per_part, dirichlet_values_per_part)
         self.extra_cellvec = extra_cellvec  # per part (ncells_integrated, nd) host-computed additive term
+        # boundary term  + ∫( v*g )dΓ  of the right-hand side (reference test/PoissonTests.jl:39): (Measure(Boundary(model,tags),degree),
+        # g) with g(x, n) -> values at the points x (D, npts) with outward unit normals n (D, npts); a dict {field: (dΓ, g)} for
+        # block systems
+        self.neumann = neumann
 
 
 class Poisson(GraftForm):
@@ -56,8 +60,8 @@ class LinearElasticity(GraftForm):
 
     form_id = L.FORM_ELASTICITY
 
-    def __init__(self, dΩ, lam, mu, source=None, extra_cellvec=None):
-        super().__init__(dΩ, source, extra_cellvec)
+    def __init__(self, dΩ, lam, mu, source=None, extra_cellvec=None, neumann=None):
+        super().__init__(dΩ, source, extra_cellvec, neumann)
         self.params = (float(lam), float(mu))
 
 
@@ -66,8 +70,8 @@ class StokesTH(GraftForm):
 
     form_id = L.FORM_STOKES
 
-    def __init__(self, dΩ, nu=1.0, source=None, extra_cellvec=None):
-        super().__init__(dΩ, source, extra_cellvec)
+    def __init__(self, dΩ, nu=1.0, source=None, extra_cellvec=None, neumann=None):
+        super().__init__(dΩ, source, extra_cellvec, neumann)
         self.params = (float(nu),)
 
 
@@ -264,6 +268,7 @@ class GraftSparseMatrixAssembler:
         self._symbolic_key = None
         self._cells_key = None
         self._matrix_generation = 0
+        self._xyz = [None] * len(self.model.models)   # node coordinates handed to graft_mesh_set_hex (None: the Cartesian ones)
         self.rows = self.cols = None
         lib = self.comm.lib
         for k, ctx in enumerate(self.comm.ctxs):
@@ -275,6 +280,7 @@ class GraftSparseMatrixAssembler:
                 xyz = np.ascontiguousarray(m.vertex_coordinates(), dtype=np.float64)
                 if perturb is not None:
                     xyz = np.ascontiguousarray(perturb(m, xyz))
+                    self._xyz[k] = xyz
                 cn = np.ascontiguousarray(m.cell_vertex_ids(), dtype=np.int32)
                 L.check(lib.graft_mesh_set_hex(ctx, m.D, len(xyz), L.ptr(xyz), len(cn), L.ptr(cn)))
             for f, (U, V) in enumerate(zip(self.trials, self.tests)):
@@ -330,7 +336,35 @@ class GraftSparseMatrixAssembler:
                 if form.extra_cellvec is not None:
                     ex = form.extra_cellvec[f][k] if isinstance(form.extra_cellvec, dict) else (form.extra_cellvec[k] if f == 0 else None)
                 L.check(lib.graft_extra_cellvec_set(ctx, f, L.ptr(np.ascontiguousarray(ex, dtype=np.float64)) if ex is not None else None))
+                nm = getattr(form, "neumann", None)
+                nm = nm.get(f) if isinstance(nm, dict) else (nm if f == 0 else None)
+                self._set_neumann(ctx, k, f, lids, nm)
         self._cells_key = [(id(trian), len(trian.cell_lids[k])) for k in range(len(self.comm.ctxs))]
+
+    def _set_neumann(self, ctx, k, f, lids, nm):
+        """graft_neumann_set: the facets of Boundary(model,tags) whose parent cell is integrated, and g at their quadrature points."""
+        lib = self.comm.lib
+        if nm is None:
+            L.check(lib.graft_neumann_set(ctx, f, 0, None, None, 0, None))
+            return
+        dΓ, gfun = nm
+        Γ, m = dΓ.trian, self.model.models[k]
+        pos = np.searchsorted(lids, Γ.cell_lids[k])
+        keep = (pos < len(lids)) & (lids[np.minimum(pos, len(lids) - 1)] == Γ.cell_lids[k]) if len(lids) else np.zeros(0, dtype=bool)
+        cells = np.ascontiguousarray(pos[keep], dtype=np.int32)
+        lfaces = np.ascontiguousarray(Γ.lfaces[k][keep], dtype=np.int32)
+        if len(cells) == 0:
+            L.check(lib.graft_neumann_set(ctx, f, 0, None, None, 0, None))
+            return
+        xyz = self._xyz[k] if self._xyz[k] is not None else m.vertex_coordinates()
+        X = xyz[m.cell_vertex_ids()[lids[cells] - 1] - 1]
+        xq, nrm = facet_points(X, lfaces, dΓ.degree)
+        nf, nqf, D = xq.shape
+        ncomp = self.trials[f].spaces[k].ncomp
+        vals = np.asarray(gfun(xq.reshape(-1, D).T, nrm.reshape(-1, D).T), dtype=np.float64)
+        vals = np.broadcast_to(vals, (ncomp, nf * nqf)) if vals.ndim < 2 else vals.reshape(ncomp, nf * nqf)
+        g = np.ascontiguousarray(vals.T.reshape(nf, nqf, ncomp))
+        L.check(lib.graft_neumann_set(ctx, f, nf, L.ptr(cells), L.ptr(lfaces), dΓ.degree, L.ptr(g)))
 
     def _prange(self, which, blk):
         lib, idx = self.comm.lib, []

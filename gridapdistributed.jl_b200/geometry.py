@@ -238,6 +238,82 @@ def Triangulation(*args):
     return DistributedTriangulation(model, lids)
 
 
+class DistributedBoundaryTriangulation:
+    """``Boundary(model,tags=...)`` (reference Geometry.jl:684-767): per part the boundary facets of the LOCAL cells whose
+    Cartesian entity carries one of the tags, as (1-based local cell id, facet of the n-cube in Gridap's order: HEX z=0, z=1,
+    y=0, y=1, x=0, x=1; QUAD y=0, y=1, x=0, x=1).  Which of them are integrated follows from the body triangulation of the
+    form (owned cells for SubAssembledRows, owned + ghost for FullyAssembledRows)."""
+
+    def __init__(self, model, tags):
+        self.model = model
+        self.cell_lids, self.lfaces = [], []
+        for m in model.models:
+            D = m.D
+            want = np.zeros(m.poly.num_entities + 1, dtype=bool)
+            for t in ([tags] if isinstance(tags, (int, str)) else list(tags)):
+                if t == "boundary":
+                    want[1:m.poly.num_entities] = True
+                else:
+                    want[int(t)] = True
+            ci = m.cell_multi_index() + m.cmin[None, :]
+            cells, lfaces = [], []
+            for lf in range(2 * D):
+                axis, side = D - 1 - lf // 2, lf % 2
+                if m.no_boundary[axis]:
+                    continue
+                mid = [1] * D
+                mid[axis] = 2 * side
+                if not want[m.poly.entity_of_mid[tuple(mid)]]:
+                    continue
+                sel = np.flatnonzero(ci[:, axis] == (m.ncells_global[axis] - 1 if side else 0))
+                cells.append(sel + 1)
+                lfaces.append(np.full(len(sel), lf))
+            cells = np.concatenate(cells) if cells else np.zeros(0, dtype=np.int64)
+            lfaces = np.concatenate(lfaces) if lfaces else np.zeros(0, dtype=np.int64)
+            order = np.lexsort((lfaces, cells))     # by cell, then by facet
+            self.cell_lids.append(cells[order].astype(np.int32))
+            self.lfaces.append(lfaces[order].astype(np.int32))
+
+
+def Boundary(model, tags="boundary"):
+    return DistributedBoundaryTriangulation(model, tags)
+
+
+def facet_points(cell_coords, lfaces, degree):
+    """Physical coordinates (nf, nqf, D) and outward unit normals (nf, nqf, D) of the facet quadrature points the library
+    integrates on (graft_neumann_set): tensor Gauss-Legendre of n = ceil((degree+1)/2) points over the facet's free axes,
+    lowest axis fastest.  This is where the caller evaluates its boundary data g(x, n) -- the lazy CellField of the
+    reference (test/PoissonTests.jl:29: ``g = n_Γn⋅∇(u)``)."""
+    X = np.asarray(cell_coords, dtype=np.float64)
+    nf, nv, D = X.shape
+    n = (int(degree) + 2) // 2
+    x1 = (np.polynomial.legendre.leggauss(n)[0] + 1.0) / 2.0
+    nqf = n ** (D - 1)
+    axis = D - 1 - np.asarray(lfaces) // 2
+    side = np.asarray(lfaces) % 2
+    xi = np.zeros((nf, nqf, D))
+    for a in range(D):
+        sel = np.flatnonzero(axis == a)
+        if len(sel) == 0:
+            continue
+        xi[sel, :, a] = side[sel, None]
+        for o, d in enumerate([d for d in range(D) if d != a]):
+            xi[np.ix_(sel, np.arange(nqf), [d])] = x1[(np.arange(nqf) // n**o) % n][None, :, None]
+    bits = np.array([[(v >> d) & 1 for d in range(D)] for v in range(nv)])
+    fac = np.where(bits[None, None, :, :] == 1, xi[:, :, None, :], 1.0 - xi[:, :, None, :])       # (nf, nqf, nv, D)
+    sgn = np.where(bits == 1, 1.0, -1.0)
+    N = fac.prod(axis=3)
+    xq = np.einsum("fqv,fvd->fqd", N, X)
+    J = np.zeros((nf, nqf, D, D))
+    for a in range(D):
+        dN = sgn[None, None, :, a] * np.prod(np.delete(fac, a, axis=3), axis=3)
+        J[:, :, :, a] = np.einsum("fqv,fvd->fqd", dN, X)
+    cof = np.linalg.det(J)[..., None, None] * np.swapaxes(np.linalg.inv(J), -1, -2)                # det(J) J^{-T}
+    nrm = cof[np.arange(nf)[:, None], np.arange(nqf)[None, :], :, axis[:, None]] * np.where(side == 1, 1.0, -1.0)[:, None, None]
+    nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    return xq, nrm
+
+
 class Measure:
     """``Measure(Ω,degree)``: tensor Gauss-Legendre, n = ceil((degree+1)/2) points per direction."""
 
@@ -276,6 +352,8 @@ __all__ = [
     "DistributedCartesianDiscreteModel",
     "Triangulation",
     "Measure",
+    "Boundary",
+    "facet_points",
     "SubAssembledRows",
     "FullyAssembledRows",
     "boundary_entity_of_nodes",

@@ -45,6 +45,7 @@ SIGNATURES = {
     "graft_csr_device": [c_vp, c_i32, c_i32, P(c_vp), P(c_vp), P(c_vp)],
     "graft_numeric": [c_vp, c_i32],
     "graft_scatter_cellmats": [c_vp, c_i32, c_i32, c_vp, c_vp],
+    "graft_neumann_set": [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp],
     "graft_cellmats_get": [c_vp, c_i32, c_i32, c_vp, c_vp],
     "graft_vec_get": [c_vp, c_i32, c_vp],
     "graft_vec_device": [c_vp, c_i32, P(c_vp)],

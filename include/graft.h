@@ -135,6 +135,18 @@ int32_t graft_state_device(graft_ctx*, int32_t field, double** d_free_values);
  * term of reference test/PoissonTests.jl:39; NULL removes it. */
 int32_t graft_extra_cellvec_set(graft_ctx*, int32_t field, const double* cellvecs);
 
+/* Boundary facet term of the right-hand side, l(v) += int_Gamma v g dGamma (reference test/PoissonTests.jl:22-39:
+ * Gamma = Boundary(model,tags="neumann"), dGamma = Measure(Gamma,degree); BoundaryTriangulation: Geometry.jl:684-767).
+ * facet_cells[f]: 0-based position of the parent cell in the integrated-cell list of graft_cells_set; facet_lfaces[f]:
+ * facet of the n-cube in Gridap's order (HEX: z=0, z=1, y=0, y=1, x=0, x=1; QUAD: y=0, y=1, x=0, x=1; SEGMENT: x=0, x=1);
+ * g: the data at the facet quadrature points, nfacets x nq_facet x ncomp, tensor Gauss-Legendre points of
+ * n = ceil((degree+1)/2) per direction over the facet's free axes (lowest axis fastest) -- evaluated by the caller,
+ * like the lazy CellField `n_Gamma . grad(u)` the reference integrates.  The library evaluates the surface measure of
+ * the facet map, the traces of the shape functions and the quadrature sums (deterministic), re-evaluates them when the
+ * node coordinates change, and adds the facet vectors to their parent cells.  nfacets = 0 removes the term. */
+int32_t graft_neumann_set(graft_ctx*, int32_t field, int64_t nfacets, const int32_t* facet_cells, const int32_t* facet_lfaces,
+                          int32_t quad_degree, const double* g_at_quadrature_points);
+
 /* ---- symbolic phase (COLLECTIVE; once per sparsity) ------------------------------------------- */
 
 /* Replaces symbolic_loop_matrix_and_vector! (FESpaces.jl:785-792), nz_counter / nz_allocation

@@ -94,6 +94,61 @@ def geometry_tables(D, xi):
     return N, dN
 
 
+def facet_quadrature(cell_coords, lfaces, quad_degree):
+    """Quadrature on boundary facets (reference ``Boundary(model,tags)`` / ``Measure(Γ,degree)``, Geometry.jl:684-767, and the
+    facet maps of Gridap's BoundaryTriangulation [ext, A.4]).  cell_coords: (nf, 2^D, D) vertices of the parent cells; lfaces: (nf,)
+    facet of the n-cube in Gridap's order (HEX: z=0, z=1, y=0, y=1, x=0, x=1; QUAD: y=0, y=1, x=0, x=1; SEGMENT: x=0, x=1).
+    Returns xi (nf, nqf, D) reference points of the parent cell, xq (nf, nqf, D) physical points, ds (nf, nqf) surface measures,
+    normals (nf, nqf, D) outward unit normals, w (nqf,) weights; facet points: tensor Gauss-Legendre over the facet's free axes,
+    lowest axis fastest."""
+    cell_coords = np.asarray(cell_coords, dtype=np.float64)
+    nf, nv, D = cell_coords.shape
+    lfaces = np.asarray(lfaces, dtype=np.int64)
+    n = (quad_degree + 2) // 2
+    x1, w1 = gauss_legendre_01(n)
+    nqf = n ** (D - 1)
+    qidx = np.stack([(np.arange(nqf) // n**o) % n for o in range(D - 1)], axis=1) if D > 1 else np.zeros((1, 0), dtype=np.int64)
+    w = np.prod(w1[qidx], axis=1) if D > 1 else np.ones(1)
+    xi = np.zeros((nf, nqf, D))
+    axis = D - 1 - lfaces // 2
+    side = lfaces % 2
+    for f in range(nf):
+        others = [d for d in range(D) if d != axis[f]]
+        xi[f, :, axis[f]] = side[f]
+        for o, d in enumerate(others):
+            xi[f, :, d] = x1[qidx[:, o]]
+    xq = np.zeros((nf, nqf, D)); ds = np.zeros((nf, nqf)); normals = np.zeros((nf, nqf, D))
+    for f in range(nf):
+        N, dN = geometry_tables(D, xi[f])
+        xq[f] = N @ cell_coords[f]
+        J = np.einsum("qva,vd->qda", dN, cell_coords[f])           # J[q][d][a] = dx_d / dxi_a
+        for q in range(nqf):
+            # Nanson: n ds = det(J) J^{-T} e_axis (reference normal of the facet, outward: -e_axis on the low side)
+            v = np.linalg.det(J[q]) * np.linalg.inv(J[q]).T[:, axis[f]] * (1.0 if side[f] else -1.0)
+            ds[f, q] = np.linalg.norm(v)
+            normals[f, q] = v / ds[f, q]
+    return xi, xq, ds, normals, w
+
+
+def integrate_boundary_facets(cell_coords, lfaces, ref_nodes, order, ncomp, quad_degree, g):
+    """Facet vectors of  ∫ v g dΓ  (the term ``∫( v*g )dΓn`` of reference test/PoissonTests.jl:39): F[f, li] = Σ_q w_q ds_q φ_li(ξ_q)
+    g[f, q, comp(li)] with the local dof order li = node + nnodes*comp (A.5).  g: (nf, nqf) or (nf, nqf, ncomp)."""
+    xi, _, ds, _, w = facet_quadrature(cell_coords, lfaces, quad_degree)
+    nf, nqf, D = xi.shape
+    tix = np.rint(np.asarray(ref_nodes) * order).astype(int)
+    nds = len(tix)
+    g = np.asarray(g, dtype=np.float64).reshape(nf, nqf, ncomp)
+    F = np.zeros((nf, nds * ncomp))
+    for f in range(nf):
+        phi = np.ones((nqf, nds))
+        for d in range(D):
+            val, _ = lagrange_1d(order, xi[f, :, d])
+            phi *= val[:, tix[:, d]]
+        for c in range(ncomp):
+            F[f, c * nds:(c + 1) * nds] = np.einsum("q,q,qi,q->i", w, ds[f], phi, g[f, :, c])
+    return F
+
+
 def integrate_cells(form, cell_coords, ref_nodes, order, ncomp, quad_degree, source=None, chunk=4096):
     """Cell matrices K[c,i,j] (test i = row, trial j = col) and vectors f[c,i] by quadrature (A.4).
 

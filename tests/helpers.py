@@ -214,3 +214,28 @@ def block_oracle_from_cell_arrays(pr, spaces, mats, vecs):
     if not vecs:
         B = None
     return orc.create_from_nz_blocks(pr.strategy, I, J, V, B, T, dofs, dofs)
+
+
+def oracle_facet_cellvecs(pr, boundary, gfun, quad_degree, perturb=None, space=None):
+    """Per part (n_integrated_cells, nd): the oracle's facet vectors of  ∫ v g dΓ  (oracle.integrate_boundary_facets) added to
+    their parent cells -- the CPU counterpart of graft_neumann_set.  boundary: g.Boundary(model, tags)."""
+    space = space or pr.U
+    out = []
+    for k, (m, s) in enumerate(zip(pr.model.models, space.spaces)):
+        lids = pr.trian.cell_lids[k]
+        X = cell_coords(m, lids)
+        if perturb is not None:
+            X = perturb(m, lids, X)
+        F = np.zeros((len(lids), s.nd))
+        pos = np.searchsorted(lids, boundary.cell_lids[k])
+        keep = (pos < len(lids)) & (lids[np.minimum(pos, len(lids) - 1)] == boundary.cell_lids[k]) if len(lids) else np.zeros(0, dtype=bool)
+        cells, lfaces = pos[keep], boundary.lfaces[k][keep]
+        if len(cells):
+            xi, xq, ds, nrm, w = orc.facet_quadrature(X[cells], lfaces, quad_degree)
+            nf, nqf, D = xq.shape
+            vals = np.asarray(gfun(xq.reshape(-1, D).T, nrm.reshape(-1, D).T), dtype=np.float64)
+            vals = np.broadcast_to(vals, (s.ncomp, nf * nqf)) if vals.ndim < 2 else vals.reshape(s.ncomp, nf * nqf)
+            Ff = orc.integrate_boundary_facets(X[cells], lfaces, s.ref_nodes, pr.order, s.ncomp, quad_degree, vals.T.reshape(nf, nqf, s.ncomp))
+            np.add.at(F, cells, Ff)
+        out.append(F)
+    return out

@@ -524,3 +524,72 @@ def test_hook1_coupled_blocks_match_oracle(parts, cells, strategy, coupling):
         L = g.libgraft
         L.check(assem.comm.lib.graft_numeric(assem.comm.handle, 3))
     assem.close()
+
+
+@pytest.mark.parametrize("strategy", ["sub", "fully"])
+def test_poisson_config1_with_device_facet_term(strategy):
+    # reference test/PoissonTests.jl:14-45 with the Neumann term ∫( v*g )dΓn integrated ON THE DEVICE (graft_neumann_set, facets.cu):
+    # Γn = Boundary(model, tags="neumann") with "neumann" = [4,6,8], dΓn = Measure(Γn, 2k), g = n_Γn⋅∇(u)
+    from helpers import oracle_facet_cellvecs
+
+    u = lambda x: (x[0] + x[1]) ** 2
+    pr = build_problem((2, 2), (4, 4), 2, [1, 2, 3, 5, 7], u, strategy, domain=[0, 4, 0, 4])
+    gN = lambda x, n: 2 * (x[0] + x[1]) * (n[0] + n[1])
+    Γn = g.Boundary(pr.model, tags=[4, 6, 8])
+    out, _ = oracle_assemble(pr, ("poisson",), source=-4.0, extra_cellvec=oracle_facet_cellvecs(pr, Γn, gN, 4))
+    st = g.FullyAssembledRows() if strategy == "fully" else g.SubAssembledRows()
+    assem = g.SparseMatrixAssembler(pr.U, pr.V, st)
+    form = g.Poisson(g.Measure(pr.trian, 4), source=-4.0, neumann=(g.Measure(Γn, 4), gN))
+    A, b = g.assemble_matrix_and_vector(form, assem)
+    assert_matches_oracle(A, b, out)
+    Ag, bg = gather_ours(A, b)
+    x = spla.spsolve(Ag.tocsc(), bg)
+    assert l2_error(pr, x, u) < 1e-9
+    # the term is removed again with the form
+    A, b2 = g.assemble_matrix_and_vector_b(A, b, g.Poisson(g.Measure(pr.trian, 4), source=-4.0), assem)
+    out0, _ = oracle_assemble(pr, ("poisson",), source=-4.0)
+    assert_matches_oracle(A, b2, out0)
+    assem.close()
+
+
+@pytest.mark.parametrize("geometry", ["cartesian", "hex", "perturbed"])
+@pytest.mark.parametrize("parts,cells,order,tags", [((2, 1, 2), (4, 3, 4), 2, [22, 24, 26]), ((1, 1, 1), (3, 3, 3), 1, "boundary"), ((2, 2), (5, 4), 2, [5, 8]),
+                                                    ((3,), (7,), 2, [2])])
+def test_device_facet_term_matches_oracle(parts, cells, order, tags, geometry):
+    # facets of general (trilinear) cells: surface measure per quadrature point; all numeric routes consume the term
+    from helpers import oracle_facet_cellvecs
+
+    D = len(cells)
+    if D == 1 and geometry == "perturbed":
+        pytest.skip("1-D cells are always affine")
+    pr = build_problem(parts, cells, order, None, None, "sub")
+    pert = g.vertex_perturbation(0.15, seed=9) if geometry == "perturbed" else None
+    operturb = (lambda m, lids, X: pert(m, m.vertex_coordinates())[m.cell_vertex_ids()[lids - 1] - 1]) if pert else None
+    gN = lambda x, n: np.sin(x[0]) * n[0] + (x[-1] ** 2 + 0.5) * n[-1] + 1.0
+    Γ = g.Boundary(pr.model, tags=tags)
+    deg = 2 * order
+    extra = oracle_facet_cellvecs(pr, Γ, gN, deg, perturb=operturb)
+    assert sum(np.abs(e).sum() for e in extra) > 0
+    out, _ = oracle_assemble(pr, ("mass",), source=0.3, extra_cellvec=extra, perturb=operturb)
+    kw = {} if geometry == "cartesian" else dict(geometry="hex", perturb=pert)
+    assem = g.SparseMatrixAssembler(pr.U, pr.V, g.SubAssembledRows(), **kw)
+    form = g.Mass(g.Measure(pr.trian, deg), source=0.3, neumann=(g.Measure(Γ, deg), gN))
+    A, b = g.assemble_matrix_and_vector(form, assem)
+    assert_matches_oracle(A, b, out)
+    assem.close()
+
+
+def test_device_facet_term_vector_valued_traction():
+    # surface traction of linear elasticity: g has one value per component
+    from helpers import oracle_facet_cellvecs
+
+    pr = build_problem((2, 1, 1), (4, 2, 2), 2, [21], _uvec(3), "sub", ncomp=3)
+    tr = lambda x, n: np.stack([0.5 * n[0] + x[1], -n[1] * x[0], 1.0 + 0 * x[0]])
+    Γ = g.Boundary(pr.model, tags=[22, 26])
+    extra = oracle_facet_cellvecs(pr, Γ, tr, 4)
+    out, _ = oracle_assemble(pr, ("elasticity", 1.3, 0.7), source=0.5, extra_cellvec=extra)
+    assem = g.SparseMatrixAssembler(pr.U, pr.V, g.SubAssembledRows())
+    form = g.LinearElasticity(g.Measure(pr.trian, 4), 1.3, 0.7, source=0.5, neumann=(g.Measure(Γ, 4), tr))
+    A, b = g.assemble_matrix_and_vector(form, assem)
+    assert_matches_oracle(A, b, out)
+    assem.close()

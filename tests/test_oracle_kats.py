@@ -302,3 +302,32 @@ def test_periodic_poisson_solution_kat(parts):
     err = l2_error(pr, x, u)
     assert err < 0.00122
     assert err > 1e-6   # a discretisation error, not an interpolation identity
+
+
+def test_facet_integration_kats():
+    """Boundary facet terms (reference test/PoissonTests.jl:22-39): the oracle's facet quadrature against closed forms and against
+    the independent 2-D helper used since round 1."""
+    from helpers import oracle_facet_cellvecs, orc
+    # surface measure and outward normals of the six faces of a sheared box
+    A = np.array([[2.0, 0.3, 0.0], [0.0, 1.5, 0.2], [0.0, 0.0, 1.0]])
+    X = np.array([[[x, y, z] for z in (0, 1) for y in (0, 1) for x in (0, 1)]], float) @ A.T
+    area = {0: np.linalg.norm(np.cross(A[:, 0], A[:, 1])), 2: np.linalg.norm(np.cross(A[:, 0], A[:, 2])), 4: np.linalg.norm(np.cross(A[:, 1], A[:, 2]))}
+    for lf in range(6):
+        xi, xq, ds, nrm, w = orc.facet_quadrature(X, [lf], 4)
+        assert abs((ds[0] * w).sum() - area[lf - lf % 2]) < 1e-12
+        inward = X[0].mean(0) - xq[0].mean(0)
+        assert (nrm[0] @ inward < 0).all() and np.allclose(np.linalg.norm(nrm[0], axis=1), 1.0)
+    # sum_i F_i = ∫_Γ g (partition of unity), g = x*y on the top face of the unit cube, Q2
+    X1 = np.array([[[x, y, z] for z in (0, 1) for y in (0, 1) for x in (0, 1)]], float)
+    xi, xq, ds, nrm, w = orc.facet_quadrature(X1, [1], 4)
+    ref = g.NCube(3).q2_ref_nodes()
+    F = orc.integrate_boundary_facets(X1, [1], ref, 2, 1, 4, (xq[..., 0] * xq[..., 1]))
+    assert abs(F.sum() - 0.25) < 1e-13
+    # the reference configuration: same cell vectors as the round-1 helper
+    u = lambda x: (x[0] + x[1]) ** 2
+    pr = build_problem((2, 2), (4, 4), 2, [1, 2, 3, 5, 7], u, "sub", domain=[0, 4, 0, 4])
+    gN = lambda x, n: 2 * (x[0] + x[1]) * (n[0] + n[1])
+    a = neumann_cellvec_2d(pr, gN)
+    b = oracle_facet_cellvecs(pr, g.Boundary(pr.model, tags=[4, 6, 8]), gN, 4)
+    for x, y in zip(a, b):
+        assert np.allclose(x, y, rtol=1e-13, atol=1e-13)
