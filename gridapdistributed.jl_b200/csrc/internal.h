@@ -339,6 +339,8 @@ struct graft_ctx {
   // this call run on vstream and finish with ev_v1
   cudaEvent_t ev_g = nullptr;
   bool ev_g_valid = false, ev_v1_used = false;
+  bool ev_g_matrix_only = false;   // block systems: only the matrix values of the ghost rows are complete at ev_g; the right-hand
+                                   // side is exchanged after the step (a second, small exchange)
   cudaEvent_t tev[8] = {nullptr};  // timing events: numeric start / integrate / scatter / exchange, spmv start / end
   bool timers_pending = false, spmv_timer_pending = false;
   Mesh mesh;
@@ -457,7 +459,10 @@ void integrate_cells_unfused(graft_ctx* ctx, int what);                     // i
 void build_entry_words(graft_ctx* x, int f, const uint32_t* cellflags);     // gather.cu
 void build_row_classes(graft_ctx* x, int bi, int bj);                       // gather.cu
 void gather_scatter_mat(graft_ctx* x, int bi, int bj, const double* cellmats, const double* cellvecs, bool with_mat, bool with_vec);
-void gather_fill_and_launch_affine(graft_ctx* x, int bi, int bj, int tier, GatherArgs& a, int ntab, bool vec);
+// phase (tier 1 with row groups, block systems over several parts): 0 = the whole block; 1 = tables + the groups of the ghost rows
+// (matrix values only); 2 = the groups of the own rows and every right-hand side kernel of the block
+void gather_fill_and_launch_affine(graft_ctx* x, int bi, int bj, int tier, GatherArgs& a, int ntab, bool vec, int phase = 0);
+bool affine_block_can_split(graft_ctx* x, int bi, int bj);   // gather.cu: tier-1 block with row groups and ghost rows at the tail
 bool fused_affine_available(graft_ctx* ctx);                                // fused.cu
 void sweep_prepare(graft_ctx* x);                                           // sweep.cu (symbolic phase, needs Space::rc_list)
 bool sweep_available(graft_ctx* x);                                         // sweep.cu

@@ -69,6 +69,35 @@ def main():
         assem.close()
         if rank == 0:
             print(f"case parts={parts} cells={cells} {strategy} {geometry}: ok on {world} ranks", flush=True)
+    # block system (Taylor-Hood Stokes): ghost rows of every block first, early exchange of the matrix values, right-hand side after
+    # the step (numeric_fused_affine phases 1 / 2); against the oracle's block pipeline on all parts
+    from helpers import stokes_oracle, stokes_problem
+
+    for strategy in ("sub", "fully"):
+        cells = tuple(2 * p for p in grid)
+        ref = stokes_problem(grid, cells, strategy)
+        out = stokes_oracle(ref, 0.7, 1.5)
+        backend = g.DistBackend()
+        pr = g.build_stokes_problem(grid, cells, strategy, backend=backend)
+        st = g.FullyAssembledRows() if strategy == "fully" else g.SubAssembledRows()
+        assem = g.SparseMatrixAssembler([pr.U, pr.P], [pr.V, pr.Q], st, device=local_rank)
+        form = g.StokesTH(g.Measure(pr.trian, 4), nu=0.7, source=1.5)
+        A, b = g.assemble_matrix_and_vector(form, assem)
+        for rep in range(2):
+            for i, j in ((0, 0), (0, 1), (1, 0)):
+                p = out[i][j][rank]
+                assert_same_prange(A[i][j].row_partition.indices[0], p["rows"], "rows")
+                assert_same_prange(A[i][j].col_partition.indices[0], p["cols"], "cols")
+                rowptr, colind, val = A[i][j].csr_arrays()[0]
+                rp, ci, v = p["csr"]
+                assert np.array_equal(rowptr, rp) and np.array_equal(colind, ci)
+                assert np.allclose(val, v, rtol=1e-12, atol=1e-12 * max(np.abs(v).max(initial=0.0), 1e-300)), f"rank {rank}: block ({i},{j}) differs"
+                if j == 0:
+                    assert np.allclose(b[i].vector_partition[0], p["b"], rtol=1e-12, atol=1e-12 * max(np.abs(p["b"]).max(initial=0.0), 1e-300))
+            A, b = g.assemble_matrix_and_vector_b(A, b, form, assem)
+        assem.close()
+        if rank == 0:
+            print(f"case Stokes parts={grid} cells={cells} {strategy}: ok on {world} ranks", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")
