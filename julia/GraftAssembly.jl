@@ -30,7 +30,8 @@ import MPI
 
 const libgraft = get(ENV, "LIBGRAFT", "libgraft")
 
-export GraftSparseMatrixAssembler, GraftForm, GraftPoisson, GraftMass, GraftLinearElasticity, GraftStokesTH, GraftPSparseMatrix, graft_solve
+export GraftSparseMatrixAssembler, GraftForm, GraftPoisson, GraftMass, GraftLinearElasticity, GraftStokesTH, GraftPSparseMatrix, graft_solve,
+       set_boundary_term!
 
 macro gcheck(ex)
   quote
@@ -260,6 +261,35 @@ function _set_form!(a::GraftSparseMatrixAssembler, form::GraftForm)
   if s !== nothing
     @gcheck ccall((:graft_source_set, libgraft), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}), a.ctx, 0, 1, s, C_NULL)
   end
+end
+
+"""
+    set_boundary_term!(a, dΓ, g)
+
+The term `∫( v*g )dΓ` of the right-hand side (test/PoissonTests.jl:22-39) for the following assemblies: `dΓ = Measure(Γ,degree)` with
+`Γ = Boundary(model,tags=...)`; `g` a CellField on Γ (e.g. `n_Γ⋅∇(u)`), evaluated here at the facet quadrature points -- the library
+integrates (surface measure, traces of the shape functions) on the device.  `nothing` removes the term.
+"""
+function set_boundary_term!(a::GraftSparseMatrixAssembler, dΓ, g; field=1)
+  if dΓ === nothing
+    @gcheck ccall((:graft_neumann_set, libgraft), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Float64}),
+                  a.ctx, field - 1, 0, C_NULL, C_NULL, 0, C_NULL)
+    return
+  end
+  Γ = dΓ.trian
+  map(local_views(Γ), local_views(a.trian), local_views(dΓ), local_views(g)) do Γl, Ωl, dΓl, gl
+    D = num_cell_dims(Ωl)
+    glue = get_glue(Γl, Val(D))                         # facet -> (parent cell of the model, local facet)
+    cell_to_pos = Dict(c => k - 1 for (k, c) in enumerate(get_glue(Ωl, Val(D)).tface_to_mface))   # model cell -> position in a.trian
+    keep = [i for (i, c) in enumerate(glue.tface_to_mface) if haskey(cell_to_pos, c)]
+    cells = Int32[cell_to_pos[glue.tface_to_mface[i]] for i in keep]
+    lfaces = Int32[glue.tface_to_lcell_lface[i] - 1 for i in keep]      # Gridap's n-cube facet order, 0-based
+    gq = evaluate(gl, get_cell_points(dΓl))                              # lazy array: per facet, g at its quadrature points
+    vals = Float64[v for i in keep for v in gq[i]]
+    @gcheck ccall((:graft_neumann_set, libgraft), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Float64}),
+                  a.ctx, field - 1, length(cells), cells, lfaces, dΓ.degree, vals)
+  end
+  nothing
 end
 
 "`assemble_matrix_and_vector(form::GraftForm, a)`: returns `(A::PSparseMatrix, b::PVector)` (blocks: `BlockPMatrix`, `BlockPVector`)."
