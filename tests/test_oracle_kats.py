@@ -331,3 +331,25 @@ def test_facet_integration_kats():
     b = oracle_facet_cellvecs(pr, g.Boundary(pr.model, tags=[4, 6, 8]), gN, 4)
     for x, y in zip(a, b):
         assert np.allclose(x, y, rtol=1e-13, atol=1e-13)
+
+
+def test_boundary_triangulation_and_facet_points_of_the_host_mirror():
+    """Host mirror of ``Boundary(model,tags)`` (reference Geometry.jl:684-767): facet counts per tag on a partitioned model, and its
+    facet quadrature points / outward normals (what the caller evaluates g on) against the oracle's, on perturbed hexes."""
+    from helpers import orc
+    pr = build_problem((2, 1, 2), (4, 3, 4), 2, None, None, "sub")
+    G = g.Boundary(pr.model, tags="boundary")
+    own = [set(ids.own_to_local.tolist()) for ids in pr.model.cell_gids.indices]
+    n_owned_facets = sum(sum(1 for c in cells if int(c) in o) for cells, o in zip(G.cell_lids, own))
+    assert n_owned_facets == 2 * (4 * 3 + 3 * 4 + 4 * 4)            # every boundary facet of the 4 x 3 x 4 box exactly once among the owned cells
+    top = g.Boundary(pr.model, tags=[22])                            # the z = 1 face only (HEX faces: 21 z=0, 22 z=1, 23 y=0, 24 y=1, 25 x=0, 26 x=1)
+    assert all((lf == 1).all() for lf in top.lfaces) and sum(sum(1 for c in cells if int(c) in o) for cells, o in zip(top.cell_lids, own)) == 12
+    per = g.CartesianDiscreteModel(g.DebugBackend(2), (2, 1), [0, 1, 0, 1], (4, 4), isperiodic=(True, False))
+    Gp = g.Boundary(per, tags="boundary")                            # a periodic direction has no boundary
+    assert all(((lf // 2) == 0).all() for lf in Gp.lfaces)           # QUAD facets 0, 1 = y faces only
+    pert = g.vertex_perturbation(0.2, seed=4)
+    for m, cells, lfaces in zip(pr.model.models, G.cell_lids, G.lfaces):
+        X = pert(m, m.vertex_coordinates())[m.cell_vertex_ids()[cells - 1] - 1]
+        xq, nrm = g.facet_points(X, lfaces, 4)
+        xi, xq2, ds, n2, w = orc.facet_quadrature(X, lfaces, 4)
+        assert np.allclose(xq, xq2, rtol=0, atol=1e-14) and np.allclose(nrm, n2, rtol=0, atol=1e-13)
