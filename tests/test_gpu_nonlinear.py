@@ -100,3 +100,18 @@ def test_newton_solution_kat():
     assert it < 19
     assert l2_error(pr, glob, u) < 1e-9
     assem.close()
+
+
+def test_state_dependent_form_on_a_cartesian_descriptor_3d_q2():
+    # 3-D Q2 p-Laplacian on a CartesianDiscreteModel handed over as a descriptor (no node coordinates): the sum-factorised integration
+    # evaluates the vertices from (origin, h); jacobian + residual against the oracle
+    u = lambda x: x[0] - x[1] + 0.5 * x[2]
+    pr = build_problem((2, 1, 1), (4, 3, 3), 2, "boundary", u, "sub", domain=[0.0, 2.0, 0.0, 1.5, 0.0, 3.0])
+    rng = np.random.default_rng(8)
+    glob = rng.uniform(-0.5, 0.5, pr.U.gids.indices[0].n_global)
+    uh = [glob[ids.l2g - 1] for ids in pr.U.gids.indices]
+    out, _ = oracle_assemble(pr, ("plaplacian",), source=0.3, state=uh)
+    assem, form, A, b = _assemble(pr, uh, 0.3)
+    assert all(s["path"] == "sumfact-gather" for s in assem.stats())
+    assert_matches_oracle(A, b, out)
+    assem.close()
