@@ -353,3 +353,71 @@ def test_boundary_triangulation_and_facet_points_of_the_host_mirror():
         xq, nrm = g.facet_points(X, lfaces, 4)
         xi, xq2, ds, n2, w = orc.facet_quadrature(X, lfaces, 4)
         assert np.allclose(xq, xq2, rtol=0, atol=1e-14) and np.allclose(nrm, n2, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("parts,cells,order", [((2, 1, 1), (4, 3, 3), 2), ((2, 2), (5, 4), 2), ((1, 2, 1), (3, 4, 3), 1)])
+def test_patch_test_on_general_cells(parts, cells, order):
+    """General (tri)linear cells -- per-quadrature-point Jacobians, the path the sum-factorised and tensor-core kernels are compared
+    with -- pinned by properties that do not depend on the oracle itself: (1) constants are in the kernel of every cell matrix and
+    the cell volumes add up to the domain; (2) the patch test: with interior vertices moved by up to 0.2 h, a LINEAR u is reproduced
+    by the isoparametric discretisation to round-off for any mesh (so the discrete solve of the assembled system returns it)."""
+    D = len(cells)
+    u = lambda x: 1.0 + sum((d + 1.5) * x[d] for d in range(D))
+    pr = build_problem(parts, cells, order, "boundary", u, "sub")
+    pert = g.vertex_perturbation(0.2, seed=11)
+    coords = lambda m, lids, X: pert(m, m.vertex_coordinates())[m.cell_vertex_ids()[lids - 1] - 1]
+    out, KF = oracle_assemble(pr, ("poisson",), source=0.0, perturb=coords)
+    vol = 0.0
+    for k, (m, s) in enumerate(zip(pr.model.models, pr.U.spaces)):
+        lids = pr.trian.cell_lids[k]
+        X = coords(m, lids, None)
+        K, _ = orc.integrate_cells(("poisson",), X, s.ref_nodes, order, 1, 2 * order)
+        assert np.abs(K.sum(2)).max() < 1e-11 and np.abs(K - K.transpose(0, 2, 1)).max() < 1e-12
+        M, _ = orc.integrate_cells(("mass",), X, s.ref_nodes, order, 1, 2 * order)
+        vol += M.sum()
+        assert not np.allclose(X, cell_coords_of(m, lids))          # the mesh really is perturbed
+    assert abs(vol - 1.0) < 1e-12                                   # boundary vertices stay: the cells still tile the unit box
+    A, b = gather_global(out)
+    x = spla.spsolve(A.tocsc(), b)
+    # nodal values of u at the free dofs of the PERTURBED mesh: isoparametric nodes follow the geometry map
+    err = 0.0
+    for k, (m, s, ids) in enumerate(zip(pr.model.models, pr.U.spaces, pr.U.gids.indices)):
+        lids = pr.trian.cell_lids[k]
+        X = coords(m, lids, None)
+        N, _ = orc.geometry_tables(D, s.ref_nodes)
+        xn = np.einsum("iv,cvd->cid", N, X)                          # physical position of every local dof node
+        cd = s.cell_dof_ids[lids - 1]
+        free = cd > 0
+        gid = ids.l2g[cd[free] - 1] - 1
+        err = max(err, np.abs(x[gid] - u(xn[free].T)).max())
+    assert err < 1e-10
+
+
+def cell_coords_of(m, lids):
+    return m.vertex_coordinates()[m.cell_vertex_ids()[lids - 1] - 1]
+
+
+def test_rigid_body_modes_of_elasticity_on_general_cells():
+    """The elasticity cell matrices of perturbed hexes annihilate the six rigid-body modes (three translations, three infinitesimal
+    rotations) -- a property of eps(u), independent of the oracle's own tables -- and are symmetric."""
+    pr = build_problem((1, 1, 1), (2, 2, 2), 2, None, None, "sub", ncomp=3)
+    m, s = pr.model.models[0], pr.U.spaces[0]
+    pert = g.vertex_perturbation(0.2, seed=2)
+    lids = pr.trian.cell_lids[0]
+    X = pert(m, m.vertex_coordinates())[m.cell_vertex_ids()[lids - 1] - 1]
+    K, _ = orc.integrate_cells(("elasticity", 1.7, 0.6), X, s.ref_nodes, 2, 3, 4)
+    N, _ = orc.geometry_tables(3, s.ref_nodes)
+    xn = np.einsum("iv,cvd->cid", N, X)                              # (ncells, 27, 3)
+    nds = xn.shape[1]
+    modes = []
+    for c in range(3):
+        t = np.zeros((len(X), 3, nds)); t[:, c] = 1.0
+        modes.append(t)
+    for a, b in ((0, 1), (1, 2), (0, 2)):
+        r = np.zeros((len(X), 3, nds)); r[:, a] = -xn[:, :, b]; r[:, b] = xn[:, :, a]
+        modes.append(r)
+    scale = np.abs(K).max()
+    for v in modes:
+        ldof = v.reshape(len(X), 3 * nds)                            # local dof = node + nnodes*comp
+        assert np.abs(np.einsum("cij,cj->ci", K, ldof)).max() < 1e-11 * scale * max(1.0, np.abs(ldof).max())
+    assert np.abs(K - K.transpose(0, 2, 1)).max() < 1e-12 * scale
