@@ -13,14 +13,14 @@ class Problem:
     pass
 
 
-def build_problem(parts, cells, order=2, tags="boundary", ufun=None, strategy="sub", domain=None, ncomp=1, backend=None):
+def build_problem(parts, cells, order=2, tags="boundary", ufun=None, strategy="sub", domain=None, ncomp=1, backend=None, isperiodic=None):
     """Single-field problem: CartesianDiscreteModel(parts, domain, cells), Lagrangian space of `order` with `ncomp`
     components, Dirichlet data `ufun` on `tags` (reference test/PoissonTests.jl:14-36)."""
     pr = Problem()
     D = len(parts)
     pr.backend = backend or DebugBackend(int(np.prod(parts)))
     pr.domain = domain if domain is not None else sum(([0.0, 1.0] for _ in cells), [])
-    pr.model = CartesianDiscreteModel(pr.backend, parts, pr.domain, cells)
+    pr.model = CartesianDiscreteModel(pr.backend, parts, pr.domain, cells, isperiodic=isperiodic)
     pr.reffe = ReferenceFE("lagrangian", float, order, ncomp=ncomp)
     pr.V = TestFESpace(pr.model, pr.reffe, dirichlet_tags=tags)
     pr.U = TrialFESpace(ufun, pr.V)

@@ -34,6 +34,20 @@ CASES = {
 }
 
 
+# Round-2 features, frozen on the CPU side only (their CUDA parity tests compare with the live oracle: tests/test_gpu_*.py):
+# general (perturbed) cells, the state-dependent p-Laplacian, a periodic model, the boundary facet term in 3-D.
+CPU_CASES = {
+    "poisson_3d_perturbed_211_sub": dict(parts=(2, 1, 1), cells=(4, 3, 3), order=2, tags="boundary", strategy="sub", domain=None, source=1.5,
+                                         neumann=False, perturbed=(0.15, 7)),
+    "plaplacian_2d_22_fully": dict(parts=(2, 2), cells=(4, 4), order=2, tags="boundary", strategy="fully", domain=[0, 4, 0, 4], source=0.7,
+                                   neumann=False, form=("plaplacian",), state_seed=5),
+    "poisson_periodic_2d_21_sub": dict(parts=(2, 1), cells=(6, 4), order=2, tags="boundary", strategy="sub", domain=None, source=1.0,
+                                       neumann=False, isperiodic=(True, False)),
+    "poisson_facets_3d_121_sub": dict(parts=(1, 2, 1), cells=(3, 4, 3), order=2, tags=[21, 23, 25], strategy="sub", domain=None, source=-1.0,
+                                      neumann=False, facet_tags=[22, 24, 26], perturbed=(0.1, 3)),
+}
+
+
 def ufun(case):
     if case.get("ncomp", 1) > 1:
         D = len(case["cells"])
@@ -45,14 +59,26 @@ def ufun(case):
 
 def build(case):
     pr = build_problem(case["parts"], case["cells"], case["order"], case["tags"], ufun(case), case["strategy"], domain=case["domain"],
-                       ncomp=case.get("ncomp", 1))
+                       ncomp=case.get("ncomp", 1), **({"isperiodic": case["isperiodic"]} if "isperiodic" in case else {}))
     extra = neumann_cellvec_2d(pr, lambda x, n: 2 * (x[0] + x[1]) * (n[0] + n[1])) if case["neumann"] else None
     return pr, extra
 
 
 def run(case):
+    from helpers import g, oracle_facet_cellvecs
+
     pr, extra = build(case)
-    out, _ = oracle_assemble(pr, case.get("form", ("poisson",)), source=case["source"], extra_cellvec=extra)
+    kw = {}
+    if "perturbed" in case:
+        pert = g.vertex_perturbation(case["perturbed"][0], seed=case["perturbed"][1])
+        kw["perturb"] = lambda m, lids, X: pert(m, m.vertex_coordinates())[m.cell_vertex_ids()[lids - 1] - 1]
+    if "state_seed" in case:
+        glob = np.random.default_rng(case["state_seed"]).uniform(-0.5, 0.5, pr.U.gids.indices[0].n_global)
+        kw["state"] = [glob[ids.l2g - 1] for ids in pr.U.gids.indices]
+    if "facet_tags" in case:
+        gfun = lambda x, n: np.cos(x[0]) * n[1] + x[2] * n[2] + 0.25
+        extra = oracle_facet_cellvecs(pr, g.Boundary(pr.model, tags=case["facet_tags"]), gfun, 2 * case["order"], perturb=kw.get("perturb"))
+    out, _ = oracle_assemble(pr, case.get("form", ("poisson",)), source=case["source"], extra_cellvec=extra, **kw)
     d = {}
     for k, p in enumerate(out):
         nown = len(p["rows"]["own_to_local"])
@@ -66,7 +92,7 @@ def run(case):
 
 
 if __name__ == "__main__":
-    for name, case in CASES.items():
+    for name, case in {**CASES, **CPU_CASES}.items():
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run(case))
