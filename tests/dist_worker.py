@@ -33,6 +33,22 @@ def main():
         assert np.array_equal(pr.U.spaces[0].cell_dof_ids, ref.U.spaces[rank].cell_dof_ids)
         assert np.allclose(pr.U.dirichlet_values[0], ref.U.dirichlet_values[rank])
         assert np.array_equal(pr.trian.cell_lids[0], ref.trian.cell_lids[rank])
+    # round-2 input producers: periodic models (reference Geometry.jl:413-459: wrapped ghost cells in the partitioned periodic
+    # direction), block spaces, and the boundary triangulation of the part
+    ref = build_problem((world, 1), (3 * world, 4), 2, "boundary", u, "sub", isperiodic=(True, False))
+    pr = build_problem((world, 1), (3 * world, 4), 2, "boundary", u, "sub", isperiodic=(True, False), backend=g.DistBackend())
+    a, b = pr.U.gids.indices[0], ref.U.gids.indices[rank]
+    assert a.n_global == b.n_global and np.array_equal(a.l2g, b.l2g) and np.array_equal(a.l2o, b.l2o)
+    assert np.array_equal(pr.U.spaces[0].cell_dof_ids, ref.U.spaces[rank].cell_dof_ids)
+    for tags in ("boundary", [6]):
+        Ga, Gb = g.Boundary(pr.model, tags=tags), g.Boundary(ref.model, tags=tags)
+        assert np.array_equal(Ga.cell_lids[0], Gb.cell_lids[rank]) and np.array_equal(Ga.lfaces[0], Gb.lfaces[rank])
+    sref = g.build_stokes_problem((world, 1), (2 * world, 2), "sub")
+    spr = g.build_stokes_problem((world, 1), (2 * world, 2), "sub", backend=g.DistBackend())
+    for fa, fb in ((spr.U, sref.U), (spr.P, sref.P)):
+        a, b = fa.gids.indices[0], fb.gids.indices[rank]
+        assert a.n_global == b.n_global and np.array_equal(a.l2g, b.l2g) and np.array_equal(a.l2o, b.l2o)
+        assert np.array_equal(fa.spaces[0].cell_dof_ids, fb.spaces[rank].cell_dof_ids)
     # backend primitives
     be = g.DistBackend()
     assert be.scan_exclusive([rank + 1]) == [sum(range(1, rank + 1))]
