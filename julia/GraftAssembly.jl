@@ -279,11 +279,11 @@ function set_boundary_term!(a::GraftSparseMatrixAssembler, dΓ, g; field=1)
   Γ = dΓ.trian
   map(local_views(Γ), local_views(a.trian), local_views(dΓ), local_views(g)) do Γl, Ωl, dΓl, gl
     D = num_cell_dims(Ωl)
-    glue = get_glue(Γl, Val(D))                         # facet -> (parent cell of the model, local facet)
+    fglue = Γl.glue                                     # FaceToCellGlue of the BoundaryTriangulation: facet -> (cell of the model, local facet)
     cell_to_pos = Dict(c => k - 1 for (k, c) in enumerate(get_glue(Ωl, Val(D)).tface_to_mface))   # model cell -> position in a.trian
-    keep = [i for (i, c) in enumerate(glue.tface_to_mface) if haskey(cell_to_pos, c)]
-    cells = Int32[cell_to_pos[glue.tface_to_mface[i]] for i in keep]
-    lfaces = Int32[glue.tface_to_lcell_lface[i] - 1 for i in keep]      # Gridap's n-cube facet order, 0-based
+    keep = [i for (i, c) in enumerate(fglue.face_to_cell) if haskey(cell_to_pos, c)]
+    cells = Int32[cell_to_pos[fglue.face_to_cell[i]] for i in keep]
+    lfaces = Int32[fglue.face_to_lface[i] - 1 for i in keep]            # Gridap's n-cube facet order, 0-based
     gq = evaluate(gl, get_cell_points(dΓl))                              # lazy array: per facet, g at its quadrature points
     vals = Float64[v for i in keep for v in gq[i]]
     @gcheck ccall((:graft_neumann_set, libgraft), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Float64}),
