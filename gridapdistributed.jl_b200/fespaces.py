@@ -60,21 +60,28 @@ class LocalFESpace:
         col = 0
         # number the faces dimension by dimension --------------------------------------------
         face_keys_in_order = []
+        nkeys = int(np.prod(hn))
+        cell_key0 = (2 * ci) @ hstride                       # key of the low corner of every cell
         for d in dims:
             mids = poly.face_mid[d]  # (nlf, D) in half units
-            hpos = (2 * ci)[:, None, :] + mids[None, :, :]
-            for dd in range(D):   # a locally periodic direction: the nodes of the far end ARE the nodes of the near end
-                if model.periodic_local[dd]:
-                    hpos[:, :, dd] = hpos[:, :, dd] % (2 * n[dd])
-            keys = hpos @ hstride  # (ncells, nlf)
+            if model.periodic_local.any():
+                hpos = (2 * ci)[:, None, :] + mids[None, :, :]
+                for dd in range(D):   # a locally periodic direction: the nodes of the far end ARE the nodes of the near end
+                    if model.periodic_local[dd]:
+                        hpos[:, :, dd] = hpos[:, :, dd] % (2 * n[dd])
+                keys = hpos @ hstride  # (ncells, nlf)
+            else:
+                keys = cell_key0[:, None] + (mids @ hstride)[None, :]
             cell_node_keys[:, col : col + len(mids)] = keys
             col += len(mids)
             flat = keys.ravel()  # cell-major, local-face order
-            if d == 0:
-                uniq = np.unique(flat)  # lexicographic vertex ids == ascending key
-            else:
-                u, first = np.unique(flat, return_index=True)
-                uniq = u[np.argsort(first, kind="stable")]  # first-appearance order
+            # the distinct keys in first-appearance order (vertices: ascending key = lexicographic vertex ids), through a table over
+            # the half-cell grid instead of a sort of all (cell, face) pairs: written backwards, the first occurrence wins
+            first = np.full(nkeys, -1, dtype=np.int64)
+            first[flat[::-1]] = np.arange(len(flat) - 1, -1, -1, dtype=np.int64)
+            uniq = np.flatnonzero(first >= 0)
+            if d > 0:
+                uniq = uniq[np.argsort(first[uniq], kind="stable")]
             face_keys_in_order.append(uniq)
         all_keys = np.concatenate(face_keys_in_order)  # node id (all dims) -> half-grid key
         nnodes = len(all_keys)
@@ -95,15 +102,18 @@ class LocalFESpace:
         node_first_dir[node_is_dir] = np.arange(ndir_nodes) * nc + 1
         self.num_free_dofs = nfree_nodes * nc
         self.num_dirichlet_dofs = ndir_nodes * nc
-        # node lookup by key
-        order = np.argsort(all_keys, kind="stable")
-        sorted_keys = all_keys[order]
-        cell_nodes = order[np.searchsorted(sorted_keys, cell_node_keys)]  # (ncells, nnodes_cell)
+        # node lookup by key (a table over the half-cell grid)
+        node_of_grid = np.full(nkeys, -1, dtype=np.int64)
+        node_of_grid[all_keys] = np.arange(nnodes, dtype=np.int64)
+        cell_nodes = node_of_grid[cell_node_keys]  # (ncells, nnodes_cell)
         ids = np.zeros((ncells, self.nd), dtype=np.int32)
+        # per node: the id of its component 0 (free > 0, Dirichlet < 0) and the direction in which the components count
+        node_id0 = np.where(node_is_dir, -node_first_dir, node_first_free).astype(np.int32)
+        node_sgn = np.where(node_is_dir, -1, 1).astype(np.int32)
+        cell_id0 = node_id0[cell_nodes]
+        cell_sgn = node_sgn[cell_nodes] if nc > 1 else None
         for c in range(nc):
-            free_id = node_first_free[cell_nodes] + c
-            dir_id = -(node_first_dir[cell_nodes] + c)
-            ids[:, c * nnodes_cell : (c + 1) * nnodes_cell] = np.where(node_is_dir[cell_nodes], dir_id, free_id)
+            ids[:, c * nnodes_cell : (c + 1) * nnodes_cell] = cell_id0 if c == 0 else cell_id0 + c * cell_sgn
         self.cell_dof_ids = np.ascontiguousarray(ids)
         # node coordinates of free and Dirichlet dofs (for interpolation of boundary data / sources)
         coords = model.local_origin()[None, :] + hidx * (model.h[None, :] / 2.0)
