@@ -1,7 +1,7 @@
 # GraftAssembly.jl -- the Julia side of the drop-in: a SparseMatrixAssembler whose symbolic / numeric phases and mul! run in
 # libgraft.so (include/graft.h) through ccall.
 #
-# STATUS: written against Gridap 0.18 / GridapDistributed 0.4.17 / PartitionedArrays 0.3 names, NOT EXECUTED IN THIS IMAGE (no
+# STATUS: written against the names of Gridap 0.20 / GridapDistributed 0.4.17 / PartitionedArrays 0.3 (reference Project.toml:19-31), NOT EXECUTED IN THIS IMAGE (no
 # julia, no package depot: SURVEY.md 8c).  What IS executed here is the same call sequence, symbol for symbol:
 #   * tests/abi_driver.c      plain C, no Python: constructor -> _set_form! -> assemble (catalogue form) -> hook 1 -> re-assembly
 #                             -> mul! -> solve, with the checks a Gridap test would make (compiled by __graft_entry__.build());
